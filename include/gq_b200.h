@@ -1,0 +1,122 @@
+/*
+ * gq_b200.h -- C ABI of libgq_b200.so: the B200 (sm_100a) GaussianQuant hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers, sizes
+ * and a CUDA stream (as void*); there are no torch types in any signature.  All calls
+ * are asynchronous on `stream`, never synchronise the device, never allocate device
+ * memory (callers pass workspaces sized by the *_workspace_bytes helpers) and return
+ * GQ_OK or a negative gq_status; gq_last_error() gives the message for the calling
+ * thread.  The caller owns every buffer.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference repo
+ * tongdaxu/VQ-VAE-from-Gaussian-VAE):
+ *
+ *   gq_scores_f32        gq_cuda_extension/gq_cuda/csrc/cuda/gq_cuda.cu:77-118  (op
+ *                        `extension_cpp::gq`, schema gq_cuda/csrc/gq_cuda.cpp:30,
+ *                        python gq_cuda/ops.py:7-8)
+ *   gq_codebook_create   pit/quantization/gaussian.py:50-52 (prior_samples / normal_log_prob
+ *                        buffers; the codebook bits themselves still come from the host's
+ *                        prior_samples(), gaussian.py:15-19)
+ *   gq_quantize          pit/quantization/gaussian.py:124-150 (both backends of the eval
+ *                        branch: score, argmax, index_select) -- fused, no [M,N] matrix
+ *   gq_quantize_exact    same semantics, CUDA-core exact-order scan (anchor / fallback)
+ *   gq_dequant           pit/quantization/gaussian.py:162-178
+ *   gq_kl_fwd/_bwd       pit/quantization/gaussian.py:76-98 (+ autograd of the same)
+ *
+ * Row convention (gaussian.py:122-123): rows M = b*l*ncb, row r = (token)*ncb + j holds
+ * channels {k*ncb + j : k < g} of its token.
+ */
+#ifndef GQ_B200_H
+#define GQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GQ_B200_ABI_VERSION 1
+
+typedef void *gq_stream_t; /* cudaStream_t */
+
+typedef enum gq_status {
+    GQ_OK = 0,
+    GQ_ERR_INVALID = -1,     /* bad argument (shape, null pointer, unsupported group) */
+    GQ_ERR_CUDA = -2,        /* a CUDA runtime call or launch failed */
+    GQ_ERR_UNSUPPORTED = -3, /* valid request this build cannot serve (e.g. not sm_100) */
+    GQ_ERR_WORKSPACE = -4    /* workspace too small */
+} gq_status;
+
+/* tensor layouts of the regularizer's latent / index tensors (gaussian.py:33,65-74) */
+typedef enum gq_layout {
+    GQ_LAYOUT_BLC = 0, /* [b, l, c]      channel innermost */
+    GQ_LAYOUT_BCHW = 1 /* [b, c, h, w]   token (h*w) innermost */
+} gq_layout;
+
+int gq_abi_version(void);
+const char *gq_last_error(void);
+/* number of kernels this library has launched in the calling process (bench accounting) */
+uint64_t gq_launch_count(void);
+
+/* ---- legacy operator: out[M,N] = sum_k( -((x-mu)/std)^2 + x*x*beta ) ------------------
+ * gq_cuda.cu:12-40.  mu,std [M,dim]; codebook [N,dim]; out [M,N]; all fp32 contiguous. */
+int gq_scores_f32(const float *mu, const float *std, const float *codebook, float *out,
+                  int64_t dim, int64_t M, int64_t N, double beta, gq_stream_t stream);
+
+/* ---- prepared codebook ---------------------------------------------------------------
+ * Device-resident, read-only after creation: the fp32 codebook [N,g], beta*normal_log_prob
+ * [N,g] and the fp16 [x^2 | x] operand image the tensor-core search streams.  `nlp` may be
+ * NULL (then Normal(0,1).log_prob is evaluated as gaussian.py:51-52 does).  The handle owns
+ * one device allocation made at creation time (not on the hot path). */
+typedef struct gq_codebook gq_codebook_t;
+int gq_codebook_create(const float *codebook, const float *nlp, int64_t N, int g, float beta,
+                       gq_stream_t stream, gq_codebook_t **out);
+void gq_codebook_destroy(gq_codebook_t *cb);
+int64_t gq_codebook_size(const gq_codebook_t *cb);
+int gq_codebook_group(const gq_codebook_t *cb);
+const float *gq_codebook_data(const gq_codebook_t *cb); /* device fp32 [N,g] */
+
+/* ---- eval-branch quantizer ------------------------------------------------------------
+ * idx[r] = first argmax_n S[r,n], S in the reference torch op order (gaussian.py:141-147);
+ * zhat[r,:] = codebook[idx[r],:] (may be NULL).  mu,std,log_std [M,g] fp32 rows
+ * (log_std = log(std) as the host framework computes it; NULL => logf in a prologue).
+ * gq_quantize: tcgen05 fp16 search with a rigorous per-row error window, exact fp32
+ * re-scoring of the surviving candidates, exact-scan fallback for ill-conditioned rows.
+ * stats (may be NULL): device uint32[8] = {rows, candidates rescored, fallback rows,
+ * overflow rows, 0...}, accumulated (caller zeroes). */
+int64_t gq_quantize_workspace_bytes(const gq_codebook_t *cb, int64_t M);
+int gq_quantize(const gq_codebook_t *cb, const float *mu, const float *std,
+                const float *log_std, int64_t M, int64_t *idx, float *zhat, void *workspace,
+                int64_t workspace_bytes, uint32_t *stats, gq_stream_t stream);
+int gq_quantize_exact(const gq_codebook_t *cb, const float *mu, const float *std,
+                      const float *log_std, int64_t M, int64_t *idx, float *zhat,
+                      gq_stream_t stream);
+
+/* ---- dequant --------------------------------------------------------------------------
+ * idx: int64, [b,l,ncb] (BLC) or [b,ncb,h,w] (BCHW); out: fp32 [b,l,ncb*g] or
+ * [b,ncb*g,h,w]; out channel k*ncb + j of a token = codebook[idx[token,j]][k].
+ * err_flag (may be NULL): device int32 set to 1 if any index is outside [0,N). */
+int gq_dequant(const gq_codebook_t *cb, const int64_t *idx, float *out, int64_t b, int64_t l,
+               int ncb, int layout, int32_t *err_flag, gq_stream_t stream);
+
+/* ---- train-branch KL penalty ------------------------------------------------------------
+ * z: fp32 [b,l,2C] or [b,2C,h,w]; eps: fp32 noise shaped like mu (torch.randn_like, kept on
+ * the host framework's RNG); zhat out = mu + eps*exp(0.5*clamp(logvar)) in z's layout.
+ * out_stats: device float[8] = {kl_loss, bits_mean, bits_min, bits_max, sum_kl2, sum_w_kl2,
+ * 0, 0}; kl_loss = lam * sum(w*kl2) / b.  w_out: fp32 [b*l*ncb] band weight per group
+ * (lam_max / 1 / lam_min), kept for backward.  workspace: gq_kl_workspace_bytes. */
+int64_t gq_kl_workspace_bytes(int64_t b, int64_t l, int C);
+int gq_kl_fwd(const float *z, const float *eps, float *zhat, float *w_out, float *out_stats,
+              int64_t b, int64_t l, int C, int g, int layout, float lv_lo, float lv_hi,
+              float target_bits, float tol, float lam, float lam_min, float lam_max,
+              void *workspace, int64_t workspace_bytes, gq_stream_t stream);
+/* grad_z = d(kl_loss)/dz * grad_kl + d(zhat)/dz . grad_zhat ; grad_kl: device scalar
+ * (may be NULL => 0), grad_zhat may be NULL => 0. */
+int gq_kl_bwd(const float *z, const float *eps, const float *w, const float *grad_zhat,
+              const float *grad_kl, float *grad_z, int64_t b, int64_t l, int C, int g,
+              int layout, float lv_lo, float lv_hi, float lam, gq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GQ_B200_H */

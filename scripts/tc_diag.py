@@ -1,0 +1,168 @@
+#!/usr/bin/env python
+"""GPU diagnostic for the tcgen05 search (development aid; run under gpurun).
+
+Dumps the raw tensor-core score tile matrix and compares it with a numpy emulation of the
+same fp16 operands, then checks gq_quantize against the CPU oracle and times a few sizes.
+Every stage runs in its own subprocess with a timeout so a hung kernel cannot eat the call.
+Results land in gpurun_out/tc_diag_*.json.
+"""
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "vq-vae-from-gaussian-vae_b200"))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+
+
+def make_rows(M, g, dist, seed=0):
+    import torch
+    gen = torch.Generator().manual_seed(seed)
+    if dist == "trained":
+        mu = torch.randn(M, g, generator=gen) * 0.866
+        lv = -1.386 + 0.3 * torch.randn(M, g, generator=gen)
+    elif dist == "randinit":
+        mu = torch.randn(M, g, generator=gen) * 0.34
+        lv = torch.randn(M, g, generator=gen) * 0.34
+    else:
+        mu = torch.randn(M, g, generator=gen)
+        lv = 2.0 * torch.log(torch.abs(torch.randn(M, g, generator=gen)) + 1e-3)
+    std = torch.exp(0.5 * lv)
+    return mu, std, std.log()
+
+
+def stage_dump(N, g, M):
+    import numpy as np
+    import torch
+    import gq_b200
+    from gq_b200 import _lib
+    from gq_b200.regularizer import prior_samples
+    cbh = prior_samples(N, g, 42).float()
+    mu, std, lstd = make_rows(M, g, "trained")
+    cb = gq_b200.Codebook(cbh.cuda(), None, 1.0)
+    L = _lib.lib()
+    L.gq_debug_plan.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+    plan = (ctypes.c_int64 * 6)()
+    L.gq_debug_plan(N, M, 148, plan)
+    units, tiles, ctas, spc, nseg, M_pad = list(plan)
+    n_pad = tiles * 128
+    ws = cb.workspace(M)
+    dump = torch.full((M_pad, n_pad), float("nan"), device="cuda")
+    wrow = torch.zeros(M_pad, device="cuda")
+    L.gq_debug_tc_scores.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 3
+    L.gq_debug_tc_scores.restype = ctypes.c_int
+    mu_d, std_d, lstd_d = mu.cuda(), std.cuda(), lstd.cuda()
+    rc = L.gq_debug_tc_scores(cb.handle, mu_d.data_ptr(), std_d.data_ptr(), lstd_d.data_ptr(), M, ws.data_ptr(),
+                              ws.numel(), dump.data_ptr(), wrow.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    res = {"rc": rc, "plan": [units, tiles, ctas, spc, nseg, M_pad]}
+    d = dump.cpu().numpy()[:M, :N]
+    w = wrow.cpu().numpy()[:M]
+    # numpy emulation of the operands
+    v = std.double().numpy() ** 2
+    a = 0.5 - 0.5 / v
+    b = mu.double().numpy() / v
+    A = np.concatenate([a, b], 1)
+    mx = np.abs(A).max(1, keepdims=True)
+    ex = np.floor(np.log2(mx)) + 1
+    s = 2.0 ** (8 - ex)
+    Ah = (A * s).astype(np.float32).astype(np.float16).astype(np.float64)
+    x = cbh.double().numpy()
+    B = np.concatenate([(cbh.numpy() * cbh.numpy()).astype(np.float64), x], 1)
+    Bh = B.astype(np.float32).astype(np.float16).astype(np.float64)
+    G = Ah @ Bh.T
+    diff = np.abs(d - G)
+    res.update({"nan_frac": float(np.isnan(d).mean()), "max_abs_diff": float(np.nanmax(diff)),
+                "max_abs_G": float(np.abs(G).max()), "w_scaled_median": float(np.median(w)),
+                "w_unscaled_median": float(np.median(w / s[:, 0])), "flagged": int((w < 0).sum())})
+    # true-score error vs window: exact G (double, unrounded) vs dump
+    Gx = (A * s) @ B.T
+    res["max_err_vs_exact_over_halfwindow"] = float(np.nanmax(np.abs(d - Gx).max(1) / (w / 2)))
+    if res["max_abs_diff"] > 0.05 * res["max_abs_G"]:
+        np.save(os.path.join(OUT, "tc_dump_bad.npy"), d[:16, :64])
+        np.save(os.path.join(OUT, "tc_dump_expected.npy"), G[:16, :64])
+        res["sample_dump"] = d[:4, :8].tolist()
+        res["sample_expected"] = G[:4, :8].tolist()
+    return res
+
+
+def stage_quantize(N, g, M, dist, exact_too=True, check_rows=4096):
+    import numpy as np
+    import torch
+    import gq_b200
+    import oracle
+    from gq_b200.regularizer import prior_samples
+    cbh = prior_samples(N, g, 42).float()
+    nlp = torch.from_numpy(oracle.normal_log_prob(cbh.numpy()))
+    mu, std, lstd = make_rows(M, g, dist)
+    cb = gq_b200.Codebook(cbh.cuda(), nlp.cuda(), 1.0)
+    mu_d, std_d, lstd_d = mu.cuda(), std.cuda(), lstd.cuda()
+    stats = torch.zeros(8, dtype=torch.int32, device="cuda")
+    idx, zhat = gq_b200.quantize_rows(cb, mu_d, std_d, lstd_d, stats=stats)
+    torch.cuda.synchronize()
+    res = {"stats": stats.cpu().tolist()}
+    # timing
+    for _ in range(3):
+        gq_b200.quantize_rows(cb, mu_d, std_d, lstd_d)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters = 10
+    for _ in range(iters):
+        gq_b200.quantize_rows(cb, mu_d, std_d, lstd_d)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    res.update({"ms": ms, "rows_per_s": M / ms * 1e3, "tflops": 4.0 * g * M * N / ms / 1e9})
+    sel = np.arange(M) if M <= check_rows else np.random.RandomState(0).choice(M, check_rows, replace=False)
+    o_idx, o_zhat, o_best, o_gap = oracle.quantize(mu.numpy()[sel], std.numpy()[sel], lstd.numpy()[sel], cbh.numpy(), nlp.numpy(), 1.0)
+    g_idx = idx.cpu().numpy()[sel]
+    mism = np.nonzero(g_idx != o_idx)[0]
+    res.update({"checked": int(len(sel)), "mismatch": int(len(mism)), "mismatch_gaps": o_gap[mism][:20].tolist(),
+                "zhat_equal": bool(np.array_equal(zhat.cpu().numpy()[sel], o_zhat))})
+    if exact_too and M <= 16384:
+        t0 = time.time()
+        idx2, _ = gq_b200.quantize_rows(cb, mu_d, std_d, lstd_d, exact=True)
+        torch.cuda.synchronize()
+        res["exact_ms"] = (time.time() - t0) * 1e3
+        res["exact_mismatch"] = int((idx2.cpu().numpy()[sel] != o_idx).sum())
+    return res
+
+
+STAGES = {
+    "dump_small": lambda: stage_dump(1024, 16, 256),
+    "dump_g4": lambda: stage_dump(4096, 4, 300),
+    "dump_64k": lambda: stage_dump(65536, 16, 1024),
+    "q_small": lambda: stage_quantize(1024, 16, 256, "trained"),
+    "q_c1": lambda: stage_quantize(65536, 16, 1024, "trained"),
+    "q_g4": lambda: stage_quantize(65536, 4, 4096, "trained"),
+    "q_g8": lambda: stage_quantize(65536, 8, 2048, "trained"),
+    "q_randinit": lambda: stage_quantize(65536, 16, 4096, "randinit"),
+    "q_stress": lambda: stage_quantize(4096, 16, 1024, "stress"),
+    "q_c2": lambda: stage_quantize(65536, 16, 65536, "trained", exact_too=False, check_rows=2048),
+    "q_256k": lambda: stage_quantize(65536, 16, 262144, "trained", exact_too=False, check_rows=1024),
+}
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--stage":
+        name = sys.argv[2]
+        r = STAGES[name]()
+        print(json.dumps({name: r}))
+        with open(os.path.join(OUT, f"tc_diag_{name}.json"), "w") as f:
+            json.dump(r, f, indent=1)
+        sys.exit(0)
+    names = sys.argv[1:] or list(STAGES)
+    for name in names:
+        t0 = time.time()
+        try:
+            p = subprocess.run([sys.executable, __file__, "--stage", name], capture_output=True, text=True, timeout=240)
+            tail = (p.stdout[-1500:] + p.stderr[-1500:]).strip()
+            print(f"[{name}] rc={p.returncode} {time.time() - t0:.1f}s\n{tail}\n", flush=True)
+        except subprocess.TimeoutExpired:
+            print(f"[{name}] TIMEOUT", flush=True)
+            break

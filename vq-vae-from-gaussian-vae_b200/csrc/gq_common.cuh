@@ -1,0 +1,111 @@
+// gq_common.cuh -- shared device helpers for libgq_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <math_constants.h>
+#include "../../include/gq_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libgq_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace gq {
+
+// math.log(math.sqrt(2*math.pi)) after torch casts the python double to fp32
+// (torch.distributions.Normal.log_prob via pit/quantization/gaussian.py:141-146).
+__device__ __constant__ static const float kC0 = 0.9189385332046727f;
+#define GQ_C0F 0.9189385332046727f
+
+constexpr int kMaxG = 32;
+
+__host__ __device__ inline int64_t imin(int64_t a, int64_t b) { return a < b ? a : b; }
+__host__ __device__ inline int64_t imax(int64_t a, int64_t b) { return a > b ? a : b; }
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char *what);
+
+// torch.sum over a contiguous innermost dim of G <= 32 fp32 values on the CPU: eight strided
+// lanes, then lanes added in order (ATen vectorized_inner_sum, Vectorized<float>::size()==8).
+// The oracle (oracle/gq_oracle.c:sum_torch_inner) is pinned bit-for-bit to the reference
+// with this order; the device code must reproduce it exactly, hence the _rn intrinsics
+// (never contracted into FMAs).
+template <int G>
+__device__ __forceinline__ float sum_torch_inner(const float (&t)[G])
+{
+    if constexpr (G < 8) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < G; ++k) acc = __fadd_rn(acc, t[k]);
+        return __fadd_rn(acc, 0.0f);
+    } else {
+        constexpr int NV = G / 8;
+        float p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = t[j];
+#pragma unroll
+            for (int v = 1; v < NV; ++v) a = __fadd_rn(a, t[j + 8 * v]);
+            p[j] = a;
+        }
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = __fadd_rn(acc, p[j]);
+        return acc;
+    }
+}
+
+// One (row, codeword) log-ratio in the reference torch op order, gaussian.py:141-147:
+//   t = x - mu ; t = t*t ; t = -t ; t = t / (2*(std*std)) ; t = t - log(std) ; t = t - c0 ;
+//   t = t - (nlp*beta) ; S = sum_k t
+// den = 2*(std*std), lstd = log(std), nlpb = nlp*beta are the invariant sub-expressions.
+template <int G>
+__device__ __forceinline__ float score_exact(const float (&x)[G], const float (&nlpb)[G],
+                                             const float (&mu)[G], const float (&den)[G],
+                                             const float (&lstd)[G])
+{
+    float t[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        float d = __fsub_rn(x[k], mu[k]);
+        float d2 = __fmul_rn(d, d);
+        float q = __fdiv_rn(-d2, den[k]);
+        float a = __fsub_rn(q, lstd[k]);
+        float b = __fsub_rn(a, GQ_C0F);
+        t[k] = __fsub_rn(b, nlpb[k]);
+    }
+    return sum_torch_inner<G>(t);
+}
+
+template <int G>
+__device__ __forceinline__ void load_row(const float *__restrict__ p, float (&v)[G])
+{
+    if constexpr (G % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < G / 4; ++k) {
+            float4 f = __ldg(reinterpret_cast<const float4 *>(p) + k);
+            v[4 * k + 0] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < G; ++k) v[k] = __ldg(p + k);
+    }
+}
+
+}  // namespace gq
+
+// opaque handle behind gq_codebook_t
+struct gq_codebook {
+    int64_t N;        // codewords
+    int g;            // group (dims per codeword)
+    int kpad;         // K of the fp16 operand image (2g rounded up to a multiple of 16)
+    int64_t n_pad;    // N rounded up to the search tile
+    float beta;
+    void *base;       // the single device allocation
+    float *cb;        // [N,g] fp32 codebook
+    float *nlpb;      // [N,g] fp32 beta*normal_log_prob (one rounding, as torch)
+    __half *bimg;     // fp16 operand image, UMMA K-major no-swizzle core-matrix order
+    float *meta;      // device floats: [0]=max ||x||^2, [1]=max ||x||, [2..2+2g) per-column max |B|
+    int device;
+};

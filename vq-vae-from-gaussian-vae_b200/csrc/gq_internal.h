@@ -1,0 +1,46 @@
+// gq_internal.h -- launch-level prototypes shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct gq_codebook;
+
+namespace gq {
+
+int launch_scores_legacy(const float *mu, const float *std, const float *cb, float *out,
+                         int64_t dim, int64_t M, int64_t N, double beta, cudaStream_t stream);
+
+int launch_quantize_exact(const gq_codebook *cb, const float *mu, const float *std,
+                          const float *lstd, int64_t M, const uint32_t *row_list,
+                          const uint32_t *row_count, int64_t *idx, float *zhat, int max_blocks,
+                          cudaStream_t stream);
+
+int launch_codebook_prep(gq_codebook *cb, const float *nlp_in, cudaStream_t stream);
+
+int launch_dequant(const gq_codebook *cb, const int64_t *idx, float *out, int64_t b, int64_t l,
+                   int ncb, int layout, int32_t *err_flag, cudaStream_t stream);
+
+// tensor-core search (gq_tc.cu)
+int64_t tc_workspace_bytes(const gq_codebook *cb, int64_t M);
+int launch_quantize_tc(const gq_codebook *cb, const float *mu, const float *std, const float *lstd,
+                       int64_t M, int64_t *idx, float *zhat, void *ws, int64_t ws_bytes,
+                       uint32_t *stats, cudaStream_t stream);
+
+int debug_tc_scores(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
+                    void *ws, int64_t ws_bytes, float *dump, float *wrow_out, cudaStream_t stream);
+void debug_plan(int64_t N, int64_t M, int sms, int64_t *out);
+
+// KL penalty (gq_kl.cu)
+int64_t kl_workspace_bytes(int64_t b, int64_t l, int C);
+int launch_kl_fwd(const float *z, const float *eps, float *zhat, float *w_out, float *out_stats,
+                  int64_t b, int64_t l, int C, int g, int layout, float lv_lo, float lv_hi,
+                  float target_bits, float tol, float lam, float lam_min, float lam_max, void *ws,
+                  int64_t ws_bytes, cudaStream_t stream);
+int launch_kl_bwd(const float *z, const float *eps, const float *w, const float *grad_zhat,
+                  const float *grad_kl, float *grad_z, int64_t b, int64_t l, int C, int g, int layout,
+                  float lv_lo, float lv_hi, float lam, cudaStream_t stream);
+
+int device_sm_count();
+int device_cc_major();
+
+}  // namespace gq

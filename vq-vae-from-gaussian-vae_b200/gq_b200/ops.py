@@ -1,0 +1,241 @@
+"""Tensor-level operators over the libgq_b200 C ABI.
+
+PyTorch is plumbing here: it owns device memory and the current stream; every operator
+below validates its tensors the way the reference wrapper does
+(gq_cuda_extension/gq_cuda/csrc/cuda/gq_cuda.cu:91-101), then hands raw device pointers to
+the C entry point on `torch.cuda.current_stream()`.  Nothing synchronises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GQ_LAYOUT_BCHW, GQ_LAYOUT_BLC, check
+
+__all__ = [
+    "Codebook", "scores_legacy_", "quantize_rows", "dequant", "kl_penalty", "launch_count",
+    "GQ_LAYOUT_BLC", "GQ_LAYOUT_BCHW",
+]
+
+_SUPPORTED_GROUPS = (1, 2, 4, 8, 16, 32)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda_f32(name: str, t: torch.Tensor) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_cuda:
+        # the reference registers no CPU kernel: calling with CPU tensors raises
+        raise NotImplementedError(f"{name} must be a CUDA tensor (no CPU implementation exists)")
+
+
+def launch_count() -> int:
+    """Kernels launched by libgq_b200 in this process so far."""
+    return int(_lib.lib().gq_launch_count())
+
+
+def scores_legacy_(mu: torch.Tensor, std: torch.Tensor, codebook: torch.Tensor, out: torch.Tensor,
+                   dim: int, M: int, N: int, beta: float) -> None:
+    """Legacy operator `extension_cpp::gq` (gq_cuda.cu:77-118): fills out[M,N] in place."""
+    for n, t in (("a", mu), ("b", std), ("c", codebook), ("out", out)):
+        _require_cuda_f32(n, t)
+    if mu.shape != std.shape:
+        raise RuntimeError("mu_q.sizes() == std_q.sizes() check failed")
+    if not out.is_contiguous():
+        raise RuntimeError("result.is_contiguous() check failed")
+    if mu.numel() != M * dim or codebook.numel() != N * dim or out.numel() != M * N:
+        raise RuntimeError(f"shape mismatch: mu {tuple(mu.shape)}, codebook {tuple(codebook.shape)}, "
+                           f"out {tuple(out.shape)} vs dim={dim} b={M} n_samples={N}")
+    mu_c, std_c, cb_c = mu.contiguous(), std.contiguous(), codebook.contiguous()
+    with torch.cuda.device(out.device):
+        check(_lib.lib().gq_scores_f32(_ptr(mu_c), _ptr(std_c), _ptr(cb_c), _ptr(out), dim, M, N,
+                                       float(beta), _stream()), "gq_scores_f32")
+
+
+class Codebook:
+    """Device-resident prepared codebook (gq_codebook_t).
+
+    `samples` is the fp32 [N, g] tensor produced by the host-side prior_samples()
+    (gaussian.py:15-19, 50); `nlp` the module's normal_log_prob buffer (gaussian.py:51-52) or
+    None to have it recomputed in the same op order."""
+
+    def __init__(self, samples: torch.Tensor, nlp: Optional[torch.Tensor] = None, beta: float = 1.0):
+        _require_cuda_f32("samples", samples)
+        if samples.dim() != 2:
+            raise RuntimeError("samples must be [N, group]")
+        N, g = samples.shape
+        if g not in _SUPPORTED_GROUPS:
+            raise RuntimeError(f"group {g} unsupported (supported: {_SUPPORTED_GROUPS})")
+        if nlp is not None:
+            _require_cuda_f32("nlp", nlp)
+            if nlp.shape != samples.shape:
+                raise RuntimeError("nlp must have the shape of samples")
+            nlp = nlp.contiguous()
+        samples = samples.contiguous()
+        self.N, self.g, self.beta, self.device = int(N), int(g), float(beta), samples.device
+        self._handle = _lib.ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gq_codebook_create(_ptr(samples), _ptr(nlp), N, g, float(beta), _stream(),
+                                                _lib.ctypes.byref(self._handle)), "gq_codebook_create")
+        self._ws = None  # cached quantize workspace (per handle, grown on demand)
+
+    @property
+    def handle(self):
+        if not self._handle:
+            raise RuntimeError("codebook handle was destroyed")
+        return self._handle
+
+    def workspace(self, M: int) -> torch.Tensor:
+        need = int(_lib.lib().gq_quantize_workspace_bytes(self.handle, M))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            _lib.lib().gq_codebook_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def quantize_rows(cb: Codebook, mu: torch.Tensor, std: torch.Tensor,
+                  log_std: Optional[torch.Tensor] = None, exact: bool = False,
+                  stats: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-branch quantizer on rows (gaussian.py:124-150): mu, std [M, g] -> (idx int64 [M],
+    zhat fp32 [M, g]).  `exact=True` runs the CUDA-core exact-order scan instead of the
+    tensor-core search (same results, used as anchor)."""
+    _require_cuda_f32("mu", mu)
+    _require_cuda_f32("std", std)
+    if mu.dim() != 2 or mu.shape != std.shape or mu.shape[1] != cb.g:
+        raise RuntimeError(f"mu/std must both be [M, {cb.g}], got {tuple(mu.shape)} / {tuple(std.shape)}")
+    if mu.device != cb.device:
+        raise RuntimeError("rows and codebook live on different devices")
+    mu, std = mu.contiguous(), std.contiguous()
+    if log_std is not None:
+        _require_cuda_f32("log_std", log_std)
+        if log_std.shape != mu.shape:
+            raise RuntimeError("log_std must have the shape of mu")
+        log_std = log_std.contiguous()
+    M = mu.shape[0]
+    idx = torch.empty(M, dtype=torch.int64, device=mu.device)
+    zhat = torch.empty(M, cb.g, dtype=torch.float32, device=mu.device)
+    if M == 0:
+        return idx, zhat
+    with torch.cuda.device(mu.device):
+        if exact:
+            check(_lib.lib().gq_quantize_exact(cb.handle, _ptr(mu), _ptr(std), _ptr(log_std), M, _ptr(idx),
+                                               _ptr(zhat), _stream()), "gq_quantize_exact")
+        else:
+            ws = cb.workspace(M)
+            check(_lib.lib().gq_quantize(cb.handle, _ptr(mu), _ptr(std), _ptr(log_std), M, _ptr(idx),
+                                         _ptr(zhat), _ptr(ws), ws.numel(), _ptr(stats), _stream()),
+                  "gq_quantize")
+    return idx, zhat
+
+
+def dequant(cb: Codebook, indices: torch.Tensor, layout: int, check_range: bool = False) -> torch.Tensor:
+    """gaussian.py:162-178.  indices int64 [b,l,ncb] (BLC) or [b,ncb,h,w] (BCHW)."""
+    if indices.dtype != torch.int64:
+        raise RuntimeError(f"indices must be int64, got {indices.dtype}")
+    if not indices.is_cuda:
+        raise NotImplementedError("indices must be a CUDA tensor (no CPU implementation exists)")
+    indices = indices.contiguous()
+    if layout == GQ_LAYOUT_BCHW:
+        if indices.dim() != 4:
+            raise RuntimeError("bchw indices must be [b, ncb, h, w]")
+        b, ncb, h, w = indices.shape
+        l = h * w
+        out = torch.empty(b, ncb * cb.g, h, w, dtype=torch.float32, device=indices.device)
+    else:
+        if indices.dim() != 3:
+            raise RuntimeError("blc indices must be [b, l, ncb]")
+        b, l, ncb = indices.shape
+        out = torch.empty(b, l, ncb * cb.g, dtype=torch.float32, device=indices.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=indices.device) if check_range else None
+    with torch.cuda.device(indices.device):
+        check(_lib.lib().gq_dequant(cb.handle, _ptr(indices), _ptr(out), b, l, ncb, layout, _ptr(flag),
+                                    _stream()), "gq_dequant")
+    if check_range and int(flag.item()):
+        raise IndexError("index out of range in dequant")  # torch.index_select raises likewise
+    return out
+
+
+class _KlPenalty(torch.autograd.Function):
+    """kl_fwd/kl_bwd pair.  Outputs (zhat, kl_loss, stats[8]); stats is non-differentiable."""
+
+    @staticmethod
+    def forward(ctx, z, eps, C, g, layout, lv_lo, lv_hi, target_bits, tol, lam, lam_min, lam_max):
+        _require_cuda_f32("z", z)
+        z = z.contiguous()
+        if layout == GQ_LAYOUT_BCHW:
+            b, c2, h, w = z.shape
+            l = h * w
+            zhat = torch.empty(b, C, h, w, dtype=torch.float32, device=z.device)
+        else:
+            b, l, c2 = z.shape
+            zhat = torch.empty(b, l, C, dtype=torch.float32, device=z.device)
+        if c2 != 2 * C:
+            raise RuntimeError("latent must carry 2*C channels (mu | logvar)")
+        if eps is not None:
+            _require_cuda_f32("eps", eps)
+            eps = eps.contiguous()
+            if eps.shape != zhat.shape:
+                raise RuntimeError("eps must have the shape of mu")
+        ncb = C // g
+        w_out = torch.empty(b * l * ncb, dtype=torch.float32, device=z.device)
+        stats = torch.empty(8, dtype=torch.float32, device=z.device)
+        L = _lib.lib()
+        ws = torch.empty(int(L.gq_kl_workspace_bytes(b, l, C)), dtype=torch.uint8, device=z.device)
+        with torch.cuda.device(z.device):
+            check(L.gq_kl_fwd(_ptr(z), _ptr(eps), _ptr(zhat), _ptr(w_out), _ptr(stats), b, l, C, g, layout,
+                              lv_lo, lv_hi, target_bits, tol, lam, lam_min, lam_max, _ptr(ws), ws.numel(),
+                              _stream()), "gq_kl_fwd")
+        ctx.save_for_backward(z, eps, w_out)
+        ctx.cfg = (b, l, C, g, layout, lv_lo, lv_hi, lam)
+        kl_loss = stats[0]
+        ctx.mark_non_differentiable(stats)
+        return zhat, kl_loss, stats
+
+    @staticmethod
+    def backward(ctx, grad_zhat, grad_kl, _grad_stats):
+        z, eps, w_out = ctx.saved_tensors
+        b, l, C, g, layout, lv_lo, lv_hi, lam = ctx.cfg
+        grad_z = torch.empty_like(z)
+        if grad_zhat is not None:
+            grad_zhat = grad_zhat.contiguous().float()
+        if grad_kl is not None:
+            grad_kl = grad_kl.contiguous().float()
+        with torch.cuda.device(z.device):
+            check(_lib.lib().gq_kl_bwd(_ptr(z), _ptr(eps), _ptr(w_out), _ptr(grad_zhat), _ptr(grad_kl),
+                                       _ptr(grad_z), b, l, C, g, layout, lv_lo, lv_hi, lam, _stream()),
+                  "gq_kl_bwd")
+        return (grad_z,) + (None,) * 11
+
+
+def kl_penalty(z: torch.Tensor, eps: Optional[torch.Tensor], group: int, layout: int,
+               logvar_range=(-30.0, 20.0), target_bits: float = 16.0, tolerance: float = 0.5,
+               lam: float = 1.0, lam_min: float = 1.0, lam_max: float = 1.0):
+    """Train-branch penalty (gaussian.py:76-98) -> (zhat, kl_loss, stats) with
+    stats = [kl_loss, bits_mean, bits_min, bits_max, sum_kl2, sum_w_kl2, 0, 0]."""
+    C = (z.shape[1] if layout == GQ_LAYOUT_BCHW else z.shape[2]) // 2
+    if C % group:
+        raise RuntimeError(f"channels {C} not divisible by group {group}")
+    return _KlPenalty.apply(z, eps, C, int(group), int(layout), float(logvar_range[0]),
+                            float(logvar_range[1]), float(target_bits), float(tolerance), float(lam),
+                            float(lam_min), float(lam_max))

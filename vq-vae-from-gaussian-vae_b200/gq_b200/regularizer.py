@@ -1,0 +1,297 @@
+"""Drop-in `GaussianQuantRegularizer` for B200.
+
+Mirrors pit/quantization/gaussian.py:22-178 of the reference -- same constructor arguments,
+same `forward(z) -> (zhat, info)` / `dequant(indices)` protocol, same `info` keys, same
+attribute names (`prior_samples`, `normal_log_prob`, `lam`, `lam_min`, `lam_max`) -- so that
+`target: pit.quantization.gaussian.GaussianQuantRegularizer` configs keep working when this
+class is bound at that path.  The hot parts run in libgq_b200:
+
+  eval  : score + argmax + gather   -> gq_quantize   (tcgen05 search + exact re-score)
+  train : KL penalty + reparam      -> gq_kl_fwd/bwd (single pass)
+  dequant: gather + permutes        -> gq_dequant
+
+There is no CPU or pure-PyTorch fallback: CPU tensors raise, a missing library fails at
+import.  `backend` is accepted for config compatibility ("torch" and "cuda" both select the
+CUDA path; anything else raises ValueError at forward time as the reference does).
+What deliberately stays in PyTorch: the codebook generator `prior_samples()` (host, once),
+`torch.randn_like` (RNG parity with the reference), and the exp/log/clamp prologue on rows
+(so std and log(std) are the framework's own values, as in the reference).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from scipy.stats import norm
+from torch.distributions import Normal
+from torch.quasirandom import SobolEngine
+
+from . import ops
+from .ops import GQ_LAYOUT_BCHW, GQ_LAYOUT_BLC, Codebook
+
+__all__ = ["prior_samples", "GaussianQuantRegularizer", "GaussianQuantRegularizer2"]
+
+
+def prior_samples(n_samples: int, n_variable: int, seed_rec: int) -> torch.Tensor:
+    """Codebook generator, kept verbatim in behaviour (gaussian.py:15-19): scrambled Sobol
+    points pushed through the normal inverse CDF on the host, float64 [n_samples, n_variable]."""
+    sobol = SobolEngine(n_variable, scramble=True, seed=seed_rec)
+    samples_sobol = sobol.draw(n_samples)
+    return torch.from_numpy(norm.ppf(samples_sobol))
+
+
+def _normal_log_prob(x: torch.Tensor) -> torch.Tensor:
+    """Normal(0, 1).log_prob(x) exactly as the reference constructor evaluates it
+    (gaussian.py:51-52), on the host, once."""
+    g = x.shape[-1]
+    return Normal(torch.zeros([1, g]), torch.ones([1, g])).log_prob(x)
+
+
+class _GQBase(nn.Module):
+    """State shared by both regularizer variants: codebook buffers + prepared device handle."""
+
+    def _init_codebook(self, n_samples: int, dim: int, seed: int, beta: float) -> None:
+        self.register_buffer("prior_samples", prior_samples(n_samples, dim, seed).float(), persistent=False)
+        self.register_buffer("normal_log_prob", _normal_log_prob(self.prior_samples).float(), persistent=False)
+        self._cb: Optional[Codebook] = None
+        self._cb_key = None
+
+    def _codebook(self) -> Codebook:
+        ps = self.prior_samples
+        if not ps.is_cuda:
+            raise NotImplementedError(
+                "GaussianQuantRegularizer (B200) has no CPU path: move the module to a CUDA device")
+        key = (ps.data_ptr(), ps.device, float(self.beta), self.normal_log_prob.data_ptr())
+        if self._cb is None or self._cb_key != key:
+            self._cb = Codebook(ps, self.normal_log_prob, float(self.beta))
+            self._cb_key = key
+        return self._cb
+
+
+class GaussianQuantRegularizer(_GQBase):
+    # train() mode: sample as Gaussian VAE, log contains loss function
+    # eval() mode: sample as VQ-VAE, log contains indices
+    def __init__(self, format, n_samples, group=1, logvar_range=[-30.0, 20.0],  # common parameters
+                 tolerance=0.5, lam_factor=1.01,  # train parameters
+                 seed=42, beta=1.0, backend="torch",  # inference parameters
+                 ):
+        super().__init__()
+        self.format = format
+        assert self.format in ["bchw", "blc"]
+        self.group = group
+        self.logvar_range = logvar_range
+        self.n_samples = n_samples
+        self.log_n_samples = int(math.log(self.n_samples, 2))
+
+        # training parameter setup (gaussian.py:40-45)
+        self.lam_factor = lam_factor
+        self.lam = 1.0
+        self.lam_min = 1.0
+        self.lam_max = 1.0
+        self.lam_range = (1e-3, 1e3)
+        self.tolerance = tolerance
+
+        # inference parameter setup (gaussian.py:48-59)
+        self.beta = beta
+        self.seed = seed
+        self._init_codebook(self.n_samples, self.group, self.seed, self.beta)
+        self.backend = backend
+        self.last_stats: Optional[torch.Tensor] = None
+
+    # -- train branch ------------------------------------------------------------------------
+    def _forward_train(self, z: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        layout = GQ_LAYOUT_BCHW if self.format == "bchw" else GQ_LAYOUT_BLC
+        if layout == GQ_LAYOUT_BCHW:
+            b, c2, h, w = z.shape
+            l, c = h * w, c2 // 2
+        else:
+            b, l, c2 = z.shape
+            c = c2 // 2
+        # the reference draws torch.randn_like(mu) with mu a [b,l,c] chunk view of the blc
+        # latent (gaussian.py:76,84); reproduce the same call so the RNG stream is identical
+        proto = torch.empty_strided((b, l, c), (l * 2 * c, 2 * c, 1), dtype=torch.float32, device=z.device)
+        eps = torch.randn_like(proto)
+        if layout == GQ_LAYOUT_BCHW:
+            eps = eps.permute(0, 2, 1).reshape(b, c, h, w)
+        zhat, kl_loss, stats = ops.kl_penalty(
+            z, eps, self.group, layout, self.logvar_range, float(self.log_n_samples), self.tolerance,
+            self.lam, self.lam_min, self.lam_max)
+        # lambda controller (gaussian.py:100-115): one device->host copy instead of three syncs
+        _, kl2_mean, kl2_min, kl2_max = stats[:4].tolist()
+        if kl2_mean > self.log_n_samples:
+            self.lam = self.lam * self.lam_factor
+        else:
+            self.lam = self.lam / self.lam_factor
+        if kl2_max > self.log_n_samples + self.tolerance:
+            self.lam_max = self.lam_max * self.lam_factor
+        else:
+            self.lam_max = self.lam_max / self.lam_factor
+        self.lam_max = max(min(self.lam_max, self.lam_range[1]), 1.0)
+        if kl2_min < self.log_n_samples - self.tolerance:
+            self.lam_min = self.lam_min / self.lam_factor
+        else:
+            self.lam_min = self.lam_min * self.lam_factor
+        self.lam_min = max(min(self.lam_min, 1.0), self.lam_range[0])
+        info = {"kl_loss": kl_loss, "bits-mean": stats[1], "bits-min": stats[2], "bits-max": stats[3],
+                "lam": torch.zeros_like(stats[0]) + self.lam}
+        return zhat, info
+
+    # -- eval branch -------------------------------------------------------------------------
+    def _forward_eval(self, z: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        if self.backend not in ("cuda", "torch"):
+            raise ValueError
+        g = self.group
+        if self.format == "bchw":
+            b, c, h, w = z.shape
+            c = c // 2
+            l = h * w
+            zhat = z.permute(0, 2, 3, 1).reshape(b, l, 2 * c)
+        else:
+            b, l, c = z.shape
+            c = c // 2
+            zhat = z
+        ncb = c // g
+        mu, logvar = zhat.chunk(2, 2)
+        logvar = torch.clamp(logvar, self.logvar_range[0], self.logvar_range[1])
+        std = torch.exp(0.5 * logvar)
+        zhat_noquant = mu + torch.randn_like(mu) * std
+        mu_r = mu.reshape(b, l, g, ncb).permute(0, 1, 3, 2).reshape(-1, g)
+        std_r = std.reshape(b, l, g, ncb).permute(0, 1, 3, 2).reshape(-1, g)
+        cb = self._codebook()
+        idx, _ = ops.quantize_rows(cb, mu_r, std_r, std_r.log(), stats=self.last_stats)
+        indices = idx.reshape(b, l, ncb)
+        if self.format == "bchw":
+            indices = indices.permute(0, 2, 1).reshape(b, ncb, h, w).contiguous()
+            zhat_noquant = zhat_noquant.permute(0, 2, 1).reshape(b, c, h, w)
+            zq = ops.dequant(cb, indices, GQ_LAYOUT_BCHW)
+        else:
+            zq = ops.dequant(cb, indices, GQ_LAYOUT_BLC)
+        return zq, {"indices": indices, "zhat_noquant": zhat_noquant}
+
+    def forward(self, z):
+        z = z.float()
+        if not z.is_cuda:
+            raise NotImplementedError(
+                "GaussianQuantRegularizer (B200) has no CPU path: pass a CUDA tensor")
+        if self.training:
+            return self._forward_train(z)
+        return self._forward_eval(z)
+
+    def dequant(self, indices):
+        layout = GQ_LAYOUT_BCHW if self.format == "bchw" else GQ_LAYOUT_BLC
+        return ops.dequant(self._codebook(), indices, layout, check_range=True)
+
+
+class GaussianQuantRegularizer2(_GQBase):
+    """Variant with contiguous grouping along `dim_idx` that runs the Gaussian and the VQ branch
+    on every forward (gaussian.py:181-362), including its quirks: mean-reduced KL (:240-241),
+    lam_range (1e-7, 1e7) (:196), and lam_max that never decreases because :251 is a no-op."""
+
+    def __init__(self, dim, codebook_size, dim_idx=1, logvar_range=[-30.0, 20.0],
+                 tolerance=0.5, lam_factor=1.01, seed=42, beta=1.0, use_ste=True, backend="torch"):
+        super().__init__()
+        self.dim_idx = dim_idx
+        self.dim = dim
+        self.logvar_range = logvar_range
+        self.n_samples = codebook_size
+        self.log_n_samples = int(math.log(self.n_samples, 2))
+        self.lam_factor = lam_factor
+        self.lam = 1.0
+        self.lam_min = 1.0
+        self.lam_max = 1.0
+        self.lam_range = (1e-7, 1e7)
+        self.tolerance = tolerance
+        self.beta = beta
+        self.seed = seed
+        self._init_codebook(self.n_samples, self.dim, self.seed, self.beta)
+        self.use_ste = use_ste
+        self.backend = backend
+
+    def quant_gaussian(self, z):
+        z = torch.movedim(z, self.dim_idx, -1)
+        assert z.shape[-1] % (self.dim * 2) == 0
+        z_shape = z.shape
+        z2 = z.reshape(-1, z_shape[-1])
+        codebook_num = z2.shape[-1] // (self.dim * 2)
+        C = codebook_num * self.dim
+        rows = z2.shape[0]
+        # contiguous grouping == the BLC kernel with ncb=1 on a [rows*codebook_num, 1, 2*dim]
+        # view whose (mu | logvar) halves are gathered per sub-codebook
+        mu, logvar = z2.chunk(2, -1)
+        eps = torch.randn_like(mu)
+        zk = torch.cat([mu.reshape(rows, codebook_num, self.dim), logvar.reshape(rows, codebook_num, self.dim)], -1)
+        zk = zk.reshape(1, rows * codebook_num, 2 * self.dim)
+        # mean-reduced loss: kl_loss = lam * mean(w*kl2) == (lam * sum(w*kl2) / 1) / count
+        zhat_k, kl_sum, stats = ops.kl_penalty(
+            zk, eps.reshape(1, rows * codebook_num, self.dim), self.dim, GQ_LAYOUT_BLC, self.logvar_range,
+            float(self.log_n_samples), self.tolerance, self.lam, self.lam_min, self.lam_max)
+        kl_loss = kl_sum / float(rows * codebook_num)
+        _, kl2_mean, kl2_min, kl2_max = stats[:4].tolist()
+        if kl2_mean > self.log_n_samples:
+            self.lam = self.lam * self.lam_factor
+        else:
+            self.lam = self.lam / self.lam_factor
+        if kl2_max > self.log_n_samples + self.tolerance:
+            self.lam_max = self.lam_max * self.lam_factor
+        # else: reference line 251 is an expression statement without assignment -> no change
+        self.lam_max = max(min(self.lam_max, self.lam_range[1]), 1.0)
+        if kl2_min < self.log_n_samples - self.tolerance:
+            self.lam_min = self.lam_min / self.lam_factor
+        else:
+            self.lam_min = self.lam_min * self.lam_factor
+        self.lam_min = max(min(self.lam_min, 1.0), self.lam_range[0])
+
+        zhat = zhat_k.reshape(rows, C).reshape(*z_shape[:-1], -1)
+        zhat = torch.movedim(zhat, -1, self.dim_idx)
+        lv = torch.clamp(logvar, self.logvar_range[0], self.logvar_range[1])
+        std = torch.exp(0.5 * lv)
+        mu_o = torch.movedim(mu.reshape(*z_shape[:-1], -1), -1, self.dim_idx)
+        std_o = torch.movedim(std.reshape(*z_shape[:-1], -1), -1, self.dim_idx)
+        info = {"kl_loss": kl_loss, "bits-mean": stats[1], "bits-min": stats[2], "bits-max": stats[3],
+                "lam-min": self.lam_min, "lam-max": self.lam_max, "lam": self.lam, "mu": mu_o, "std": std_o,
+                "zhat_noquant": zhat}
+        return zhat, info
+
+    def quant_vq(self, z):
+        if self.backend not in ("cuda", "torch"):
+            raise ValueError
+        z = torch.movedim(z, self.dim_idx, -1)
+        assert z.shape[-1] % (self.dim * 2) == 0
+        z_shape = z.shape
+        z2 = z.reshape(-1, z_shape[-1])
+        codebook_num = z2.shape[-1] // (self.dim * 2)
+        mu, logvar = z2.chunk(2, -1)
+        logvar = torch.clamp(logvar, self.logvar_range[0], self.logvar_range[1])
+        std = torch.exp(0.5 * logvar)
+        mu = mu.reshape(-1, self.dim)
+        std = std.reshape(-1, self.dim)
+        idx, zq = ops.quantize_rows(self._codebook(), mu, std, std.log())
+        zhat = zq.reshape(-1, codebook_num * self.dim).reshape(*z_shape[:-1], -1)
+        zhat = torch.movedim(zhat, -1, self.dim_idx)
+        indices = idx.reshape(-1, codebook_num).reshape(*z_shape[:-1], -1)
+        indices = torch.movedim(indices, -1, self.dim_idx)
+        return zhat, {"indices": indices, "zhat_quant": zhat}
+
+    def forward(self, z):
+        if not z.is_cuda:
+            raise NotImplementedError(
+                "GaussianQuantRegularizer2 (B200) has no CPU path: pass a CUDA tensor")
+        zhat_g, info_g = self.quant_gaussian(z)
+        with torch.no_grad():
+            zhat_v, info_v = self.quant_vq(z)
+        if self.use_ste:
+            zhat = zhat_g - zhat_g.detach() + zhat_v
+        else:
+            zhat = zhat_g if self.training else zhat_v
+        return zhat, info_g | info_v
+
+    def dequant(self, indices):
+        indices = torch.movedim(indices, self.dim_idx, -1)
+        i_shape = indices.shape
+        codebook_num = i_shape[-1]
+        flat = indices.reshape(1, -1, 1).contiguous()
+        zhat = ops.dequant(self._codebook(), flat, GQ_LAYOUT_BLC, check_range=True)
+        zhat = zhat.reshape(-1, codebook_num * self.dim).reshape(*i_shape[:-1], -1)
+        return torch.movedim(zhat, -1, self.dim_idx)
