@@ -1,0 +1,290 @@
+"""CUDA path (through the libgq_b200 C ABI) vs the CPU oracle and the reference goldens.
+
+Bars: indices / dequant bit-exact; KL within 1e-5 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import EVAL_CASES, TRAIN_CASES, golden_codebook, load_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def gq():
+    import gq_b200
+    return gq_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def trained_rows(M, g, seed=0, dist="trained"):
+    gen = torch.Generator().manual_seed(seed)
+    if dist == "trained":
+        mu = torch.randn(M, g, generator=gen) * 0.866
+        lv = -1.386 + 0.3 * torch.randn(M, g, generator=gen)
+    elif dist == "randinit":
+        mu = torch.randn(M, g, generator=gen) * 0.34
+        lv = torch.randn(M, g, generator=gen) * 0.34
+    else:  # stress: gq_cuda_extension/test/test_extension.py:18-19
+        mu = torch.randn(M, g, generator=gen)
+        lv = 2.0 * torch.log(torch.abs(torch.randn(M, g, generator=gen)) + 1e-3)
+    std = torch.exp(0.5 * lv)
+    return mu, std, std.log()
+
+
+_CB = {}
+
+
+def big_codebook(gq, N, g, beta=1.0):
+    key = (N, g, beta)
+    if key not in _CB:
+        from gq_b200.regularizer import prior_samples
+        cb = prior_samples(N, g, 42).float()
+        nlp = torch.from_numpy(oracle.normal_log_prob(cb.numpy()))
+        _CB[key] = (cb, nlp, gq.Codebook(cb.cuda(), nlp.cuda(), beta))
+    return _CB[key]
+
+
+# ---- quantizer: golden fixtures ---------------------------------------------------------------
+@pytest.mark.parametrize("exact", [False, True], ids=["tc", "exact"])
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_quantize_rows_golden(gq, name, exact):
+    g = load_golden(name)
+    cb_np, nlp_np = golden_codebook(g)
+    cb = gq.Codebook(dev(cb_np), dev(nlp_np), float(g["beta"]))
+    idx, zhat = gq.quantize_rows(cb, dev(g["mu_rows"]), dev(g["std_rows"]), dev(g["log_std_rows"]), exact=exact)
+    o_idx, o_zhat, _, _ = oracle.quantize(g["mu_rows"], g["std_rows"], g["log_std_rows"], cb_np, nlp_np, float(g["beta"]))
+    assert idx.dtype == torch.int64
+    assert np.array_equal(idx.cpu().numpy(), o_idx)          # bit-exact indices
+    assert np.array_equal(zhat.cpu().numpy(), o_zhat)        # bit-exact codewords
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_module_eval_golden(gq, name):
+    """Drop-in module: z -> (zhat, indices) must equal the reference's outputs.  exp/log run in
+    torch on the GPU here and on the CPU in the fixture, so rows whose std differs by an ulp
+    could move a near-tie; count mismatches and require every one to be a near-tie."""
+    g = load_golden(name)
+    reg = gq.GaussianQuantRegularizer(format=str(g["format"]), n_samples=int(g["n_samples"]), group=int(g["group"]),
+                                      beta=float(g["beta"]), backend="cuda").cuda().eval()
+    cb_np, _ = golden_codebook(g)
+    assert np.array_equal(reg.prior_samples.cpu().numpy(), cb_np)
+    zhat, info = reg(dev(g["z"]))
+    assert info["indices"].dtype == torch.int64 and info["indices"].shape == g["indices"].shape
+    assert zhat.shape == g["zhat"].shape and info["zhat_noquant"].shape == g["zhat_noquant"].shape
+    ind = info["indices"].cpu().numpy()
+    mism = ind != g["indices"]
+    if mism.any():
+        fmt = str(g["format"])
+        gap = g["gap"]
+        if fmt == "bchw":
+            b, ncb, h, w = ind.shape
+            gap = gap.reshape(b, h * w, ncb).transpose(0, 2, 1).reshape(b, ncb, h, w)
+        else:
+            gap = gap.reshape(ind.shape)
+        assert (gap[mism] < 1e-4).all(), f"index mismatch on a non-tie: gaps {gap[mism]}"
+    else:
+        assert np.array_equal(zhat.cpu().numpy(), g["zhat"])
+    # the invariant the reference's self-test prints: dequant(indices) == zhat
+    assert torch.equal(reg.dequant(info["indices"]), zhat)
+
+
+# ---- quantizer: seeded rows vs oracle at growing sizes ----------------------------------------------
+@pytest.mark.parametrize("N,g,M,dist", [
+    (4096, 16, 1, "trained"), (4096, 16, 7, "trained"), (4096, 16, 257, "trained"),
+    (65536, 16, 1024, "trained"),     # BASELINE configs[0]
+    (65536, 16, 2048, "randinit"),
+    (65536, 4, 4096, "trained"),      # sd3unet_gq_1.00 sub-codebooks
+    (65536, 8, 2048, "trained"),
+    (4096, 16, 512, "stress"),        # test_extension.py distribution: exercises the fallback
+    (1000, 16, 300, "trained"),       # N not a multiple of the tile
+    (262144, 16, 512, "trained"),     # sweep upper end
+])
+def test_quantize_rows_vs_oracle(gq, N, g, M, dist):
+    cb, nlp, h = big_codebook(gq, N, g)
+    mu, std, lstd = trained_rows(M, g, seed=N % 97 + M, dist=dist)
+    stats = torch.zeros(8, dtype=torch.int32, device="cuda")
+    idx, zhat = gq.quantize_rows(h, mu.cuda(), std.cuda(), lstd.cuda(), stats=stats)
+    o_idx, o_zhat, _, o_gap = oracle.quantize(mu.numpy(), std.numpy(), lstd.numpy(), cb.numpy(), nlp.numpy())
+    got = idx.cpu().numpy()
+    bad = np.nonzero(got != o_idx)[0]
+    assert len(bad) == 0, f"{len(bad)} mismatches, gaps {o_gap[bad][:8]}, stats {stats.cpu().tolist()}"
+    assert np.array_equal(zhat.cpu().numpy(), o_zhat)
+    assert int(stats[0]) == M
+
+
+def test_quantize_full_size_properties(gq):
+    """BASELINE configs[1] size (M = 64 img * 1024 tokens, N = 65536): the oracle checks a row
+    sample bit-exactly; size-independent properties cover the rest (idempotence: quantizing a
+    codeword with tiny std returns that codeword; determinism; zhat == codebook[idx])."""
+    N, g, M = 65536, 16, 65536
+    cb, nlp, h = big_codebook(gq, N, g)
+    mu, std, lstd = trained_rows(M, g, seed=11)
+    idx, zhat = gq.quantize_rows(h, mu.cuda(), std.cuda(), lstd.cuda())
+    idx2, _ = gq.quantize_rows(h, mu.cuda(), std.cuda(), lstd.cuda())
+    assert torch.equal(idx, idx2)
+    assert torch.equal(zhat, cb.cuda()[idx])
+    sel = np.random.RandomState(3).choice(M, 4096, replace=False)
+    o_idx, _, _, _ = oracle.quantize(mu.numpy()[sel], std.numpy()[sel], lstd.numpy()[sel], cb.numpy(), nlp.numpy())
+    assert np.array_equal(idx.cpu().numpy()[sel], o_idx)
+    # idempotence: mu = a codeword, std small but well-conditioned -> that codeword wins
+    pick = torch.from_numpy(np.random.RandomState(4).choice(N, 2048, replace=False))
+    mu_c = cb[pick].clone()
+    std_c = torch.full_like(mu_c, 0.05)
+    idx_c, _ = gq.quantize_rows(h, mu_c.cuda(), std_c.cuda(), std_c.log().cuda())
+    assert torch.equal(idx_c.cpu(), pick)
+
+
+def test_quantize_empty(gq):
+    _, _, h = big_codebook(gq, 4096, 16)
+    e = torch.zeros(0, 16, device="cuda")
+    idx, zhat = gq.quantize_rows(h, e, e, e)
+    assert idx.shape == (0,) and zhat.shape == (0, 16)
+
+
+# ---- legacy operator ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["legacy_b1", "legacy_b07"])
+def test_legacy_op_bit_exact_vs_oracle(gq, name):
+    import gq_cuda
+    g = load_golden(name)
+    M, dim = g["mu"].shape
+    N = g["noise"].shape[0]
+    out = torch.zeros(M, N, device="cuda")
+    gq_cuda.ops.gq_cuda(dev(g["mu"]), dev(g["std"]), dev(g["noise"]), out, dim, M, N, float(g["beta"]))
+    want = oracle.scores_legacy(g["mu"], g["std"], g["noise"], float(g["beta"]), contract=True)
+    assert np.array_equal(out.cpu().numpy(), want)
+    np.testing.assert_allclose(out.cpu().numpy(), g["result"], rtol=2e-5, atol=2e-3)  # test_extension.py:5-6
+
+
+def test_legacy_op_errors(gq):
+    import gq_cuda
+    a = torch.zeros(4, 16, device="cuda")
+    c = torch.zeros(32, 16, device="cuda")
+    with pytest.raises(RuntimeError):
+        gq_cuda.ops.gq_cuda(a, torch.zeros(3, 16, device="cuda"), c, torch.zeros(4, 32, device="cuda"), 16, 4, 32, 1.0)
+    with pytest.raises(RuntimeError):
+        gq_cuda.ops.gq_cuda(a.double(), a.double(), c, torch.zeros(4, 32, device="cuda"), 16, 4, 32, 1.0)
+    with pytest.raises(RuntimeError):
+        gq_cuda.ops.gq_cuda(a, a, c, torch.zeros(32, 4, device="cuda").t(), 16, 4, 32, 1.0)
+    with pytest.raises(NotImplementedError):
+        gq_cuda.ops.gq_cuda(a.cpu(), a.cpu(), c.cpu(), torch.zeros(4, 32), 16, 4, 32, 1.0)
+
+
+def test_legacy_then_argmax_equals_fused(gq):
+    """gaussian.py:124-133 (legacy backend) and the fused path pick the same codewords."""
+    N, g, M = 4096, 16, 512
+    cb, nlp, h = big_codebook(gq, N, g)
+    mu, std, lstd = trained_rows(M, g, seed=5)
+    import gq_cuda
+    out = torch.zeros(M, N, device="cuda")
+    gq_cuda.ops.gq_cuda(mu.cuda(), std.cuda(), cb.cuda(), out, g, M, N, 1.0)
+    idx_legacy = torch.argmax(out, dim=1)
+    idx, _ = gq.quantize_rows(h, mu.cuda(), std.cuda(), lstd.cuda())
+    _, _, _, gap = oracle.quantize(mu.numpy(), std.numpy(), lstd.numpy(), cb.numpy(), nlp.numpy())
+    diff = (idx_legacy != idx).cpu().numpy()
+    assert (gap[diff] < 1e-3).all()      # the two score forms differ only by fp32 rounding
+
+
+# ---- dequant ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_dequant_golden(gq, name):
+    g = load_golden(name)
+    cb_np, nlp_np = golden_codebook(g)
+    cb = gq.Codebook(dev(cb_np), dev(nlp_np), float(g["beta"]))
+    layout = gq.ops.GQ_LAYOUT_BCHW if str(g["format"]) == "bchw" else gq.ops.GQ_LAYOUT_BLC
+    out = gq.dequant(cb, dev(g["indices"]), layout, check_range=True)
+    assert np.array_equal(out.cpu().numpy(), g["dequant"])
+
+
+def test_dequant_out_of_range(gq):
+    _, _, h = big_codebook(gq, 4096, 16)
+    bad = torch.full((1, 4, 1), 4096, dtype=torch.int64, device="cuda")
+    with pytest.raises(IndexError):
+        gq.dequant(h, bad, gq.ops.GQ_LAYOUT_BLC, check_range=True)
+    with pytest.raises(RuntimeError):
+        gq.dequant(h, bad.int(), gq.ops.GQ_LAYOUT_BLC)
+
+
+# ---- KL penalty ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_kl_forward_backward_golden(gq, name):
+    g = load_golden(name)
+    fmt = str(g["format"])
+    layout = gq.ops.GQ_LAYOUT_BCHW if fmt == "bchw" else gq.ops.GQ_LAYOUT_BLC
+    for s in range(int(g["steps"])):
+        z = dev(g[f"z{s}"]).requires_grad_(True)
+        zhat_ref = g[f"zhat{s}"]
+        lam, lam_min, lam_max = [float(v) for v in g[f"lam_before{s}"]]
+        # recover the reference's eps from its zhat so that the backward can be compared
+        zr = g[f"z{s}"]
+        C = zr.shape[1] // 2 if fmt == "bchw" else zr.shape[2] // 2
+        mu = zr[:, :C] if fmt == "bchw" else zr[..., :C]
+        lv = np.clip(zr[:, C:] if fmt == "bchw" else zr[..., C:], -30.0, 20.0)
+        eps = (zhat_ref - mu) / np.exp(0.5 * lv)
+        zhat, kl, stats = gq.kl_penalty(z, dev(eps.astype(np.float32)), int(g["group"]), layout, (-30.0, 20.0), 16.0, 0.5,
+                                        lam, lam_min, lam_max)
+        st = stats.cpu().numpy()
+        assert float(kl) == pytest.approx(float(g[f"kl_loss{s}"]), rel=1e-5)
+        assert st[1] == pytest.approx(float(g[f"bits_mean{s}"]), rel=1e-5)
+        assert st[2] == pytest.approx(float(g[f"bits_min{s}"]), rel=1e-5, abs=1e-5)
+        assert st[3] == pytest.approx(float(g[f"bits_max{s}"]), rel=1e-5)
+        np.testing.assert_allclose(zhat.detach().cpu().numpy(), zhat_ref, rtol=1e-5, atol=1e-5)
+        loss = 0.1 * kl + (zhat * dev(g[f"wz{s}"])).sum()
+        loss.backward()
+        gr = z.grad.cpu().numpy()
+        ref = g[f"grad{s}"]
+        scale = np.abs(ref).max()
+        np.testing.assert_allclose(gr, ref, rtol=2e-4, atol=2e-6 * scale)
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_module_train_lambda_controller(gq, name):
+    g = load_golden(name)
+    reg = gq.GaussianQuantRegularizer(format=str(g["format"]), n_samples=int(g["n_samples"]), group=int(g["group"]),
+                                      backend="cuda").cuda().train()
+    for s in range(int(g["steps"])):
+        zhat, info = reg(dev(g[f"z{s}"]))
+        assert set(info) == {"kl_loss", "bits-mean", "bits-min", "bits-max", "lam"}
+        assert float(info["kl_loss"]) == pytest.approx(float(g[f"kl_loss{s}"]), rel=1e-5)
+        assert float(info["lam"]) == pytest.approx(float(g[f"lam_info{s}"]), rel=1e-6)
+        np.testing.assert_allclose([reg.lam, reg.lam_min, reg.lam_max], g[f"lam_after{s}"], rtol=1e-12)
+        assert zhat.shape == g[f"zhat{s}"].shape
+
+
+def test_kl_full_size_vs_oracle(gq):
+    """BASELINE configs[3] shape: z [256, 1024, 32] blc."""
+    gen = torch.Generator().manual_seed(0)
+    mu = torch.randn(256, 1024, 16, generator=gen) * 0.866
+    lv = -1.386 + 0.3 * torch.randn(256, 1024, 16, generator=gen)
+    z = torch.cat([mu, lv], 2)
+    zhat, kl, stats = gq.kl_penalty(z.cuda(), None, 16, gq.ops.GQ_LAYOUT_BLC, (-30.0, 20.0), 16.0, 0.5, 1.3, 0.7, 2.0)
+    r = oracle.kl(z.numpy(), 16, 16, 0.5, 1.3, 0.7, 2.0)
+    st = stats.cpu().numpy()
+    assert float(kl) == pytest.approx(r["kl_loss"], rel=1e-5)
+    assert st[1] == pytest.approx(r["bits_mean"], rel=1e-5)
+    assert st[2] == pytest.approx(r["bits_min"], rel=1e-5)
+    assert st[3] == pytest.approx(r["bits_max"], rel=1e-5)
+    assert torch.equal(zhat.cpu(), mu)     # eps=None -> zhat = mu
+
+
+# ---- GaussianQuantRegularizer2 ("next" row of SURVEY 8f) ----------------------------------------------------
+@pytest.mark.parametrize("name", ["gq2_bchw_dim16", "gq2_blc_dim8"])
+def test_gq2_golden(gq, name):
+    g = load_golden(name)
+    reg = gq.GaussianQuantRegularizer2(dim=int(g["dim"]), codebook_size=int(g["n_samples"]), dim_idx=int(g["dim_idx"]),
+                                       backend="cuda").cuda().eval()
+    assert np.array_equal(reg.prior_samples.cpu().numpy(), g["codebook"])
+    zhat, info = reg(dev(g["z"]))
+    assert np.array_equal(info["indices"].cpu().numpy(), g["indices"])
+    assert np.array_equal(info["zhat_quant"].cpu().numpy(), g["zhat_quant"])
+    assert float(info["kl_loss"]) == pytest.approx(float(g["kl_loss"]), rel=1e-5)
+    assert float(info["bits-mean"]) == pytest.approx(float(g["bits_mean"]), rel=1e-5)
+    np.testing.assert_allclose([reg.lam, reg.lam_min, reg.lam_max], g["lam_after"], rtol=1e-12)
+    assert np.array_equal(reg.dequant(info["indices"]).cpu().numpy(), g["dequant"])
+    # STE output: zhat_g - zhat_g.detach() + zhat_v == zhat_v up to one rounding of the cancel
+    np.testing.assert_allclose(zhat.detach().cpu().numpy(), g["zhat_quant"], rtol=0, atol=1e-5)
