@@ -116,6 +116,21 @@ int gq_kl_bwd(const float *z, const float *eps, const float *w, const float *gra
               const float *grad_kl, float *grad_z, int64_t b, int64_t l, int C, int g,
               int layout, float lv_lo, float lv_hi, float lam, gq_stream_t stream);
 
+/* ---- measurement and diagnostics (no reference counterpart) ------------------------------
+ * gq_profile_enable(1): every later gq_quantize records a CUDA-event pair around its search
+ * kernel on the caller's stream; gq_profile_read sums and clears them (synchronises on the
+ * recorded events).  gq_set_window_max: rows whose rigorous error window exceeds `w` (score
+ * units) go to the exact scan (default 3.0).  gq_debug_tc_scores dumps the raw tensor-core
+ * score matrix [M_pad, n_pad] and the scaled per-row windows [M_pad]; gq_debug_plan returns
+ * the stream-K decomposition {units, tiles, ctas, steps_per_cta, nseg, M_pad}. */
+void gq_profile_enable(int on);
+int gq_profile_read(double *total_ms, int *count);
+void gq_set_window_max(float w);
+int gq_debug_tc_scores(const gq_codebook_t *cb, const float *mu, const float *std,
+                       const float *log_std, int64_t M, void *workspace, int64_t workspace_bytes,
+                       float *dump, float *wrow_out, gq_stream_t stream);
+void gq_debug_plan(int64_t N, int64_t M, int sms, int64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,8 +1,9 @@
 """In-tree build of libgq_b200.so (nvcc, sm_100a only).
 
-    python -m gq_b200.build            # from vq-vae-from-gaussian-vae_b200/
+    python vq-vae-from-gaussian-vae_b200/build_ext.py [--force] [-v]
 
-The shared object lands next to this file so that it travels with the source tree.
+Stand-alone on purpose (it must not import gq_b200, whose import loads the library).  The
+shared object lands in gq_b200/ so that it travels with the source tree.
 """
 from __future__ import annotations
 
@@ -12,7 +13,7 @@ import subprocess
 import sys
 from pathlib import Path
 
-PKG_DIR = Path(__file__).resolve().parent
+PKG_DIR = Path(__file__).resolve().parent / "gq_b200"
 CSRC = PKG_DIR.parent / "csrc"
 LIB = PKG_DIR / "libgq_b200.so"
 SOURCES = ["gq_api.cu", "gq_kernels.cu", "gq_kl.cu", "gq_tc.cu"]

@@ -68,7 +68,10 @@ uint64_t gq_launch_count(void) { return g_launches.load(std::memory_order_relaxe
  * window above which a row is routed to the exact scan. */
 void gq_set_window_max(float w) { set_tc_window_max(w); }
 
-/* diagnostics used by tests/ only (not declared in include/gq_b200.h) */
+void gq_profile_enable(int on) { prof_enable(on); }
+int gq_profile_read(double *total_ms, int *count) { return prof_read(total_ms, count); }
+
+/* diagnostics used by tests/ and scripts/ only */
 int gq_debug_tc_scores(const gq_codebook_t *cb, const float *mu, const float *std, const float *log_std, int64_t M,
                        void *workspace, int64_t workspace_bytes, float *dump, float *wrow_out, gq_stream_t stream)
 {

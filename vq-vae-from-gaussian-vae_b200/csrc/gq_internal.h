@@ -30,6 +30,9 @@ int debug_tc_scores(const gq_codebook *cb, const float *mu, const float *std, co
                     void *ws, int64_t ws_bytes, float *dump, float *wrow_out, cudaStream_t stream);
 void debug_plan(int64_t N, int64_t M, int sms, int64_t *out);
 
+void prof_enable(int on);
+int prof_read(double *total_ms, int *count);
+
 // KL penalty (gq_kl.cu)
 int64_t kl_workspace_bytes(int64_t b, int64_t l, int C);
 int launch_kl_fwd(const float *z, const float *eps, float *zhat, float *w_out, float *out_stats,

@@ -13,25 +13,54 @@
 //                         the prepared [x^2 | x] codebook image through a shared-memory ring,
 //                         one thread issues tcgen05.mma (fp16 x fp16 -> fp32, M=128, N=128,
 //                         K=2g) into four TMEM accumulators, eight epilogue warps pull tiles
-//                         with tcgen05.ld and keep a running row maximum with FMNMX3; a chunk
-//                         whose maximum comes within W_r of the running maximum appends its
-//                         qualifying columns to the row's candidate list.
-//   3. rescore_kernel     per row: drop candidates below (final max - W_r), evaluate the rest
-//                         in the reference's exact fp32 op order, first-max tie-break, write
-//                         idx (int64) and zhat.  Rows whose window is too wide, that overflow
+//                         with tcgen05.ld (the whole 32x128 tile of a warp into registers, so
+//                         the TMEM stage is released before any math) and keep a running row
+//                         maximum with FMNMX3; a 32-column chunk whose maximum comes within
+//                         W_r of the running maximum is recorded as (max, chunk id).
+//   3. rescore_kernel     one warp per row: drop chunk records below (final max - W_r), score
+//                         the 32 codewords of every surviving chunk (lane = codeword) in the
+//                         reference's exact fp32 op order, first-max tie-break, write idx
+//                         (int64) and zhat.  Rows whose window is too wide, that overflow
 //                         their list, or that contain non-finite values go to
 //   4. quantize_exact_kernel (gq_kernels.cu) through a device-side row list.
 //
 // Why the result is exactly the reference argmax: with E_r >= |G~[n]/s - (S_ref[n] - Q_r)| for
 // all n (Q_r constant in n), the reference argmax n* satisfies
 // G~[n*] >= G~[m] - 2 s E_r for every m, in particular for the running maxima the epilogue
-// compares against (each is some G~[m]); so n* is always appended, survives the final filter,
-// and wins the exact re-scoring.  DESIGN.md ("error window") derives E_r.
+// compares against (each is some G~[m]); so the chunk holding n* is always recorded (its maximum
+// is >= G~[n*]), survives the final filter, and n* wins the exact re-scoring of that chunk.
+// DESIGN.md ("error window") derives E_r.
 #include "gq_common.cuh"
 #include "gq_internal.h"
 #include "gq_ptx.cuh"
 
+#include <utility>
+#include <vector>
+
 namespace gq {
+
+// ---- optional per-launch timing of the search kernel (bench.py's roofline leg) ----------------
+static bool g_prof = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+void prof_enable(int on) { g_prof = on != 0; }
+int prof_read(double *total_ms, int *count)
+{
+    double tot = 0.0;
+    int n = 0;
+    for (auto &pr : g_prof_events) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            tot += ms;
+            ++n;
+        }
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    g_prof_events.clear();
+    if (total_ms) *total_ms = tot;
+    if (count) *count = n;
+    return GQ_OK;
+}
 
 using namespace gq::ptx;
 
@@ -44,11 +73,12 @@ constexpr int kAccStages = 2;        // TMEM accumulator stages per row block
 constexpr int kTmemCols = 512;       // 2 row blocks x 2 stages x 128 fp32 columns
 constexpr int kThreads = 384;        // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;
-constexpr int kCap = 32;             // candidate slots per (row, segment)
+constexpr int kCap = 32;             // chunk records per (row, segment)
+constexpr int kChunk = 32;           // columns per recorded chunk
 constexpr int kMinStepsPerCta = 8;
 
 struct __align__(8) SegHdr { float runmax; uint32_t cnt; };
-struct __align__(8) Cand { float score; uint32_t idx; };
+struct __align__(8) Cand { float score; uint32_t idx; };  // idx = chunk id (codeword / 32)
 
 struct TcPlan {
     int64_t M, M_pad, N;
@@ -223,46 +253,25 @@ __device__ __forceinline__ bool next_piece(int64_t &step, int64_t end, int tiles
 }
 
 // Running-max epilogue for one chunk of 32 consecutive columns held in v[0..31].
-// Fast path: 16 FMNMX3 + 2 for the group maxima, one compare.  Slow path (chunk maximum within
-// the window of the running maximum): update the running max / threshold, append qualifying
-// columns.
-__device__ __forceinline__ void epi_chunk(const float *v, uint32_t col0, uint32_t n_valid, float w,
-                                          float &runmax, float &thr, uint32_t &cnt, Cand *__restrict__ list)
+// Fast path: 16 FMNMX3/FMNMX and one compare.  Slow path (chunk maximum within the window of the
+// running maximum, ~10 times per row over 2048 chunks): raise the running max / threshold and
+// record (chunk max, chunk id); the rescoring kernel re-derives the candidates of the chunk.
+__device__ __forceinline__ float chunk_max32(const float *v)
 {
-    float m8[4];
-#pragma unroll
-    for (int g8 = 0; g8 < 4; ++g8) {
-        const float *u = v + 8 * g8;
-        float a = max3(u[0], u[1], u[2]);
-        float b = max3(u[3], u[4], u[5]);
-        m8[g8] = max3(a, b, fmaxf(u[6], u[7]));
-    }
-    float m = fmaxf(max3(m8[0], m8[1], m8[2]), m8[3]);
-    if (m >= thr) {
-        // columns >= n_valid are codebook padding (zero operand rows): mask them out
-        if (col0 + 32 > n_valid) {
-            m = -CUDART_INF_F;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (col0 + i < n_valid) m = fmaxf(m, v[i]);
-            if (!(m >= thr)) return;
-        }
-        if (m > runmax) { runmax = m; thr = runmax - w; }
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-            if (m8[g8] >= thr) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float s = v[8 * g8 + i];
-                    uint32_t col = col0 + 8 * g8 + i;
-                    if (s >= thr && col < n_valid) {
-                        if (cnt < (uint32_t)kCap) list[cnt] = Cand{s, col};
-                        ++cnt;
-                    }
-                }
-            }
-        }
-    }
+    float a0 = max3(v[0], v[1], v[2]), a1 = max3(v[3], v[4], v[5]), a2 = max3(v[6], v[7], v[8]);
+    float a3 = max3(v[9], v[10], v[11]), a4 = max3(v[12], v[13], v[14]), a5 = max3(v[15], v[16], v[17]);
+    float a6 = max3(v[18], v[19], v[20]), a7 = max3(v[21], v[22], v[23]), a8 = max3(v[24], v[25], v[26]);
+    float a9 = max3(v[27], v[28], v[29]), a10 = fmaxf(v[30], v[31]);
+    float b0 = max3(a0, a1, a2), b1 = max3(a3, a4, a5), b2 = max3(a6, a7, a8), b3 = fmaxf(a9, a10);
+    return fmaxf(max3(b0, b1, b2), b3);
+}
+
+__device__ __forceinline__ void epi_record(float m, uint32_t chunk, float w, float &runmax, float &thr,
+                                           uint32_t &cnt, Cand *__restrict__ list)
+{
+    if (m > runmax) { runmax = m; thr = m - w; }
+    if (cnt < (uint32_t)kCap) list[cnt] = Cand{m, chunk};
+    ++cnt;
 }
 
 template <int KPAD, bool DUMP>
@@ -274,13 +283,15 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 {
     using L = TcSmem<KPAD>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kBarOff);
-    uint64_t *full_b = bars;
-    uint64_t *empty_b = bars + kStages;
-    uint64_t *a_full = bars + 2 * kStages;
-    uint64_t *a_empty = a_full + 2;
-    uint64_t *acc_full = a_empty + 2;   // [rb*2 + stage]
-    uint64_t *acc_empty = acc_full + 4;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + L::kBarOff;
+    // barrier addresses (shared-window u32), computed once
+    auto full_b = [&](int i) { return bar_base + 8u * i; };
+    auto empty_b = [&](int i) { return bar_base + 8u * (kStages + i); };
+    auto a_full = [&](int i) { return bar_base + 8u * (2 * kStages + i); };
+    auto a_empty = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };
+    auto acc_full = [&](int i) { return bar_base + 8u * (2 * kStages + 4 + i); };   // [rb*2 + stage]
+    auto acc_empty = [&](int i) { return bar_base + 8u * (2 * kStages + 8 + i); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kSlotOff);
 
     const int warp = threadIdx.x >> 5;
@@ -290,9 +301,10 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     const int64_t step_end = imin(step_begin + steps_per_cta, total_steps);
 
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kBarOff);
+        for (int i = 0; i < 2 * kStages + 4; ++i) mbar_init(&bars[i], 1);           // full_b, empty_b, a_full, a_empty
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[2 * kStages + 4 + i], 1);       // acc_full
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[2 * kStages + 8 + i], 4);       // acc_empty: 4 epilogue warps
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -314,17 +326,17 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             int pi = 0;
             while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
                 const int ab = pi & 1;
-                mbar_wait(&a_empty[ab], ((pi >> 1) & 1) ^ 1);
-                mbar_expect_tx(&a_full[ab], L::kABytes);
-                bulk_g2s(smem + L::kAOff + ab * L::kABytes,
-                         reinterpret_cast<const char *>(a_img) + (int64_t)p.unit * L::kABytes, L::kABytes,
-                         &a_full[ab]);
+                mbar_wait_a(a_empty(ab), ((pi >> 1) & 1) ^ 1);
+                mbar_expect_tx_a(a_full(ab), L::kABytes);
+                bulk_g2s_a(smem_base + L::kAOff + ab * L::kABytes,
+                           reinterpret_cast<const char *>(a_img) + (int64_t)p.unit * L::kABytes, L::kABytes,
+                           a_full(ab));
                 for (int t = p.t0; t < p.t1; ++t) {
-                    mbar_wait(&empty_b[stage], phase ^ 1);
-                    mbar_expect_tx(&full_b[stage], L::kBTileBytes);
-                    bulk_g2s(smem + L::kBOff + stage * L::kBTileBytes,
-                             reinterpret_cast<const char *>(b_img) + (int64_t)t * L::kBTileBytes,
-                             L::kBTileBytes, &full_b[stage]);
+                    mbar_wait_a(empty_b(stage), phase ^ 1);
+                    mbar_expect_tx_a(full_b(stage), L::kBTileBytes);
+                    bulk_g2s_a(smem_base + L::kBOff + stage * L::kBTileBytes,
+                               reinterpret_cast<const char *>(b_img) + (int64_t)t * L::kBTileBytes,
+                               L::kBTileBytes, full_b(stage));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 ++pi;
@@ -336,8 +348,8 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockRows, kTileN);
             constexpr uint32_t kLbo = 128;              // K-adjacent core matrices
             constexpr uint32_t kSbo = (KPAD / 8) * 128; // next 8-row group
-            const uint32_t a_base = smem_u32(smem + L::kAOff);
-            const uint32_t b_base = smem_u32(smem + L::kBOff);
+            const uint32_t a_base = smem_base + L::kAOff;
+            const uint32_t b_base = smem_base + L::kBOff;
             int64_t step = step_begin;
             Piece p;
             int stage = 0;
@@ -347,13 +359,13 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             int pi = 0;
             while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
                 const int ab = pi & 1;
-                mbar_wait(&a_full[ab], (pi >> 1) & 1);
+                mbar_wait_a(a_full(ab), (pi >> 1) & 1);
                 for (int t = p.t0; t < p.t1; ++t) {
-                    mbar_wait(&full_b[stage], phase);
+                    mbar_wait_a(full_b(stage), phase);
                     tc_fence_after();
 #pragma unroll
                     for (int rb = 0; rb < 2; ++rb) {
-                        mbar_wait(&acc_empty[rb * 2 + as], aphase ^ 1);
+                        mbar_wait_a(acc_empty(rb * 2 + as), aphase ^ 1);
                         tc_fence_after();
                         const uint32_t d = tmem_base + (uint32_t)((rb * kAccStages + as) * kTileN);
                         const uint32_t a_addr = a_base + ab * L::kABytes + rb * (kBlockRows * KPAD * 2);
@@ -364,22 +376,23 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                             uint64_t bd = umma_desc_kmajor_noswz(b_addr + j * 256, kLbo, kSbo);
                             umma_f16_ss(d, ad, bd, idesc, j > 0 ? 1u : 0u);
                         }
-                        umma_commit(&acc_full[rb * 2 + as]);
+                        umma_commit_a(acc_full(rb * 2 + as));
                     }
-                    umma_commit(&empty_b[stage]);
+                    umma_commit_a(empty_b(stage));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                     as ^= 1;
                     if (as == 0) aphase ^= 1;
                 }
-                umma_commit(&a_empty[ab]);
+                umma_commit_a(a_empty(ab));
                 ++pi;
             }
         }
     } else if (warp >= kEpiWarp0) {
-        // ===== epilogue: TMEM -> registers, running row max, candidate capture =====
+        // ===== epilogue: TMEM -> registers, running row max, chunk records =====
         const int ew = warp - kEpiWarp0;
         const int rb = ew >> 2;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const bool padded = (N % kTileN) != 0;
         int64_t step = step_begin;
         Piece p;
         int as = 0;
@@ -392,30 +405,45 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             uint32_t cnt = 0;
             Cand *list = cand + (row * nseg + p.seg) * (int64_t)kCap;
             for (int t = p.t0; t < p.t1; ++t) {
-                mbar_wait(&acc_full[rb * 2 + as], aphase);
+                mbar_wait_a(acc_full(rb * 2 + as), aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
                                        (uint32_t)((rb * kAccStages + as) * kTileN);
-                const uint32_t n0 = (uint32_t)t * kTileN;
-                const uint32_t n_valid = (uint32_t)imin(N, (int64_t)0xffffffffu);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v[64];
-                    tmem_ld_32x64_sync(taddr + h * 64, v);
-                    if constexpr (DUMP) {
-                        // debug build only: spill the raw tensor-core scores [M_pad, tiles*128]
-                        float *drow = dump + row * ((int64_t)tiles * kTileN) + n0 + h * 64;
-#pragma unroll
-                        for (int i = 0; i < 64; ++i) drow[i] = v[i];
-                    }
-                    epi_chunk(v, n0 + h * 64, n_valid, w, runmax, thr, cnt, list);
-                    epi_chunk(v + 32, n0 + h * 64 + 32, n_valid, w, runmax, thr, cnt, list);
-                }
+                float v[128];
+                tmem_ld_32x128_sync(taddr, v);
+                // the tile now lives in registers: hand the TMEM stage back before doing any math
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[rb * 2 + as]);
+                if (lane == 0) mbar_arrive_a(acc_empty(rb * 2 + as));
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
+
+                if constexpr (DUMP) {
+                    // debug build only: spill the raw tensor-core scores [M_pad, tiles*128]
+                    float *drow = dump + row * ((int64_t)tiles * kTileN) + (int64_t)t * kTileN;
+#pragma unroll
+                    for (int i = 0; i < 128; ++i) drow[i] = v[i];
+                }
+                const uint32_t chunk0 = (uint32_t)t * (kTileN / kChunk);
+                if (padded && t == tiles - 1) {
+                    // last tile of a codebook that is not a multiple of 128: columns >= N hold the
+                    // zero padding rows of the operand image and must not raise the running max
+                    const int n_in_tile = (int)(N - (int64_t)t * kTileN);
+#pragma unroll
+                    for (int c = 0; c < kTileN / kChunk; ++c) {
+                        float m = -CUDART_INF_F;
+#pragma unroll
+                        for (int i = 0; i < kChunk; ++i)
+                            if (c * kChunk + i < n_in_tile) m = fmaxf(m, v[c * kChunk + i]);
+                        if (m >= thr && c * kChunk < n_in_tile) epi_record(m, chunk0 + c, w, runmax, thr, cnt, list);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < kTileN / kChunk; ++c) {
+                        const float m = chunk_max32(v + c * kChunk);
+                        if (m >= thr) epi_record(m, chunk0 + c, w, runmax, thr, cnt, list);
+                    }
+                }
             }
             seg_hdr[row * nseg + p.seg] = SegHdr{runmax, cnt};
         }
@@ -429,94 +457,98 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     }
 }
 
-// ---- 3. exact re-scoring of the candidates ------------------------------------------------------
+// ---- 3. exact re-scoring of the recorded chunks: one warp per row, lane = codeword -----------------
+constexpr int kRescoreWarps = 4;
+
 template <int G>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kRescoreWarps * 32)
 rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
                const float *__restrict__ cb, const float *__restrict__ nlpb, const float *__restrict__ wrow,
-               const SegHdr *__restrict__ seg_hdr, const Cand *__restrict__ cand, int64_t M, int tiles,
+               const SegHdr *__restrict__ seg_hdr, const Cand *__restrict__ cand, int64_t M, int64_t N, int tiles,
                int steps_per_cta, int nseg, int64_t *__restrict__ idx_out, float *__restrict__ zhat_out,
                uint32_t *__restrict__ fb_rows, uint32_t *__restrict__ fb_count, uint32_t *__restrict__ stats)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= M) return;
-    const float w = wrow[r];
-    bool fallback = !(w >= 0.f);
-    uint32_t n_rescored = 0, overflow = 0;
-    int best_idx = -1;
-    if (!fallback) {
-        const int unit = (int)(r / kUnitRows);
-        const int64_t s0 = (int64_t)unit * tiles;
-        const int first = (int)(s0 / steps_per_cta);
-        const int last = (int)((s0 + tiles - 1) / steps_per_cta);
-        const int npieces = last - first + 1;
-        float gmax = -CUDART_INF_F;
-        for (int s = 0; s < npieces; ++s) {
-            SegHdr h = seg_hdr[r * nseg + s];
-            gmax = fmaxf(gmax, h.runmax);
-            if (h.cnt > (uint32_t)kCap) overflow = 1;
-        }
-        if (overflow || !(gmax > -CUDART_INF_F)) fallback = true;
-        else {
-            const float thr = gmax - w;
-            float m[G], den[G], ls[G];
-            load_row<G>(mu + r * G, m);
-            {
-                float sd[G];
-                load_row<G>(std + r * G, sd);
-#pragma unroll
-                for (int k = 0; k < G; ++k) {
-                    den[k] = __fmul_rn(2.0f, __fmul_rn(sd[k], sd[k]));
-                    ls[k] = lstd ? __ldg(lstd + r * G + k) : logf(sd[k]);
-                }
-            }
-            float best = -CUDART_INF_F;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (int64_t)blockIdx.x * kRescoreWarps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kRescoreWarps;
+    uint32_t st_rows = 0, st_resc = 0, st_fb = 0, st_ovf = 0;
+
+    for (int64_t r = warp_global; r < M; r += nwarps) {
+        const float w = wrow[r];
+        bool fallback = !(w >= 0.f);
+        bool overflow = false;
+        int best_idx = 0x7fffffff;
+        float best = -CUDART_INF_F;
+        if (!fallback) {
+            const int unit = (int)(r / kUnitRows);
+            const int64_t s0 = (int64_t)unit * tiles;
+            const int first = (int)(s0 / steps_per_cta);
+            const int last = (int)((s0 + tiles - 1) / steps_per_cta);
+            const int npieces = last - first + 1;
+            float gmax = -CUDART_INF_F;
             for (int s = 0; s < npieces; ++s) {
-                const uint32_t cnt = seg_hdr[r * nseg + s].cnt;
-                const Cand *list = cand + (r * nseg + s) * (int64_t)kCap;
-                for (uint32_t i = 0; i < cnt; ++i) {
-                    Cand c = list[i];
-                    if (!(c.score >= thr)) continue;
-                    float x[G], nb[G];
-                    load_row<G>(cb + (int64_t)c.idx * G, x);
-                    load_row<G>(nlpb + (int64_t)c.idx * G, nb);
-                    float sc = score_exact<G>(x, nb, m, den, ls);
-                    ++n_rescored;
-                    if (sc > best || (sc == best && (int)c.idx < best_idx) || best_idx < 0) {
-                        if (best_idx < 0 || sc > best || (sc == best && (int)c.idx < best_idx)) {
-                            best = sc;
-                            best_idx = (int)c.idx;
+                SegHdr h = seg_hdr[r * nseg + s];
+                gmax = fmaxf(gmax, h.runmax);
+                if (h.cnt > (uint32_t)kCap) overflow = true;
+            }
+            if (overflow || !(gmax > -CUDART_INF_F)) fallback = true;
+            else {
+                const float thr = gmax - w;
+                float m[G], den[G], ls[G];
+                load_row<G>(mu + r * G, m);
+                {
+                    float sd[G];
+                    load_row<G>(std + r * G, sd);
+#pragma unroll
+                    for (int k = 0; k < G; ++k) {
+                        den[k] = __fmul_rn(2.0f, __fmul_rn(sd[k], sd[k]));
+                        ls[k] = lstd ? __ldg(lstd + r * G + k) : logf(sd[k]);
+                    }
+                }
+                for (int s = 0; s < npieces; ++s) {
+                    const uint32_t cnt = seg_hdr[r * nseg + s].cnt;
+                    const Cand *list = cand + (r * nseg + s) * (int64_t)kCap;
+                    for (uint32_t i = 0; i < cnt; ++i) {
+                        const Cand c = list[i];            // warp-uniform
+                        if (!(c.score >= thr)) continue;
+                        const int64_t n = (int64_t)c.idx * kChunk + lane;
+                        st_resc += 1;
+                        if (n < N) {
+                            float x[G], nb[G];
+                            load_row<G>(cb + n * G, x);
+                            load_row<G>(nlpb + n * G, nb);
+                            const float sc = score_exact<G>(x, nb, m, den, ls);
+                            if (sc > best || (sc == best && (int)n < best_idx)) { best = sc; best_idx = (int)n; }
                         }
                     }
                 }
-            }
-            if (best_idx < 0 || !(best > -CUDART_INF_F)) fallback = true;  // NaN/-inf scores: let the scan decide
-        }
-    }
-    if (fallback) {
-        uint32_t slot = atomicAdd(fb_count, 1u);
-        fb_rows[slot] = (uint32_t)r;
-    } else {
-        idx_out[r] = (int64_t)best_idx;
-        if (zhat_out) {
-            float x[G];
-            load_row<G>(cb + (int64_t)best_idx * G, x);
 #pragma unroll
-            for (int k = 0; k < G; ++k) zhat_out[r * G + k] = x[k];
+                for (int off = 16; off > 0; off >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
+                    if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+                }
+                if (best_idx == 0x7fffffff || !(best > -CUDART_INF_F)) fallback = true;  // NaN / -inf rows: let the scan decide
+            }
         }
+        if (fallback) {
+            if (lane == 0) {
+                uint32_t slot = atomicAdd(fb_count, 1u);
+                fb_rows[slot] = (uint32_t)r;
+            }
+            st_fb += 1;
+        } else {
+            if (lane == 0) idx_out[r] = (int64_t)best_idx;
+            if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
+        }
+        st_rows += 1;
+        st_ovf += overflow ? 1u : 0u;
     }
-    if (stats) {
-        // warp-aggregated statistics
-        uint32_t a = __reduce_add_sync(__activemask(), n_rescored);
-        uint32_t f = __reduce_add_sync(__activemask(), fallback ? 1u : 0u);
-        uint32_t o = __reduce_add_sync(__activemask(), overflow);
-        uint32_t c = __popc(__activemask());
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&stats[0], c);
-            atomicAdd(&stats[1], a);
-            atomicAdd(&stats[2], f);
-            atomicAdd(&stats[3], o);
-        }
+    if (stats && lane == 0) {
+        atomicAdd(&stats[0], st_rows);
+        atomicAdd(&stats[1], st_resc * 32u);
+        atomicAdd(&stats[2], st_fb);
+        atomicAdd(&stats[3], st_ovf);
     }
 }
 
@@ -542,14 +574,28 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
     int rc = check_launch("rows_prep_kernel");
     if (rc) return rc;
 
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (g_prof) {
+        cudaEventCreate(&ev0);
+        cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, stream);
+    }
     quantize_tc_kernel<KPAD, false><<<p.ctas, kThreads, L::kBytes, stream>>>(
         w.a_img, cb->bimg, w.wrow, w.seg, w.cand, cb->N, p.tiles, p.total_steps, p.steps_per_cta, p.nseg, nullptr);
+    if (g_prof) {
+        cudaEventRecord(ev1, stream);
+        g_prof_events.emplace_back(ev0, ev1);
+    }
     rc = check_launch("quantize_tc_kernel");
     if (rc) return rc;
 
-    rescore_kernel<G><<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(
-        mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.seg, w.cand, M, p.tiles, p.steps_per_cta, p.nseg, idx, zhat,
-        w.fb_rows, w.counters, stats);
+    {
+        int64_t need = (M + kRescoreWarps - 1) / kRescoreWarps;
+        int blocks = (int)imin(need, (int64_t)device_sm_count() * 16);
+        rescore_kernel<G><<<blocks, kRescoreWarps * 32, 0, stream>>>(
+            mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.seg, w.cand, M, cb->N, p.tiles, p.steps_per_cta, p.nseg, idx,
+            zhat, w.fb_rows, w.counters, stats);
+    }
     rc = check_launch("rescore_kernel");
     if (rc) return rc;
     count_launch(3);

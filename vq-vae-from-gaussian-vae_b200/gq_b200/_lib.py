@@ -43,8 +43,13 @@ PROTOTYPES = {
                           c_void_p, c_int64, c_void_p]),
     "gq_kl_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                           c_int64, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
-    # tuning hook, not part of the reference-facing surface
+    # measurement / diagnostics (no reference counterpart)
+    "gq_profile_enable": (None, [c_int]),
+    "gq_profile_read": (c_int, [POINTER(c_double), POINTER(c_int)]),
     "gq_set_window_max": (None, [c_float]),
+    "gq_debug_tc_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                   c_void_p, c_void_p, c_void_p]),
+    "gq_debug_plan": (None, [c_int64, c_int64, c_int, POINTER(c_int64)]),
 }
 
 _lib = None
@@ -60,7 +65,7 @@ def lib() -> ctypes.CDLL:
     if _lib is None:
         if not LIB_PATH.exists():
             raise ImportError(
-                f"{LIB_PATH} is missing: build it with `python -m gq_b200.build` "
+                f"{LIB_PATH} is missing: build it with `python vq-vae-from-gaussian-vae_b200/build_ext.py` "
                 "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
         l = ctypes.CDLL(str(LIB_PATH))
         for name, (res, args) in PROTOTYPES.items():

@@ -24,9 +24,6 @@ from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn as nn
-from scipy.stats import norm
-from torch.distributions import Normal
-from torch.quasirandom import SobolEngine
 
 from . import ops
 from .ops import GQ_LAYOUT_BCHW, GQ_LAYOUT_BLC, Codebook
@@ -34,19 +31,7 @@ from .ops import GQ_LAYOUT_BCHW, GQ_LAYOUT_BLC, Codebook
 __all__ = ["prior_samples", "GaussianQuantRegularizer", "GaussianQuantRegularizer2"]
 
 
-def prior_samples(n_samples: int, n_variable: int, seed_rec: int) -> torch.Tensor:
-    """Codebook generator, kept verbatim in behaviour (gaussian.py:15-19): scrambled Sobol
-    points pushed through the normal inverse CDF on the host, float64 [n_samples, n_variable]."""
-    sobol = SobolEngine(n_variable, scramble=True, seed=seed_rec)
-    samples_sobol = sobol.draw(n_samples)
-    return torch.from_numpy(norm.ppf(samples_sobol))
-
-
-def _normal_log_prob(x: torch.Tensor) -> torch.Tensor:
-    """Normal(0, 1).log_prob(x) exactly as the reference constructor evaluates it
-    (gaussian.py:51-52), on the host, once."""
-    g = x.shape[-1]
-    return Normal(torch.zeros([1, g]), torch.ones([1, g])).log_prob(x)
+from gq_b200_host import normal_log_prob as _normal_log_prob, prior_samples  # noqa: E402,F401
 
 
 class _GQBase(nn.Module):
@@ -100,6 +85,23 @@ class GaussianQuantRegularizer(_GQBase):
         self.backend = backend
         self.last_stats: Optional[torch.Tensor] = None
 
+    def _update_lambdas(self, kl2_mean: float, kl2_min: float, kl2_max: float) -> None:
+        """The stateful host-side controller, gaussian.py:100-115, fed with python floats."""
+        if kl2_mean > self.log_n_samples:
+            self.lam = self.lam * self.lam_factor
+        else:
+            self.lam = self.lam / self.lam_factor
+        if kl2_max > self.log_n_samples + self.tolerance:
+            self.lam_max = self.lam_max * self.lam_factor
+        else:
+            self.lam_max = self.lam_max / self.lam_factor
+        self.lam_max = max(min(self.lam_max, self.lam_range[1]), 1.0)
+        if kl2_min < self.log_n_samples - self.tolerance:
+            self.lam_min = self.lam_min / self.lam_factor
+        else:
+            self.lam_min = self.lam_min * self.lam_factor
+        self.lam_min = max(min(self.lam_min, 1.0), self.lam_range[0])
+
     # -- train branch ------------------------------------------------------------------------
     def _forward_train(self, z: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
         layout = GQ_LAYOUT_BCHW if self.format == "bchw" else GQ_LAYOUT_BLC
@@ -120,20 +122,7 @@ class GaussianQuantRegularizer(_GQBase):
             self.lam, self.lam_min, self.lam_max)
         # lambda controller (gaussian.py:100-115): one device->host copy instead of three syncs
         _, kl2_mean, kl2_min, kl2_max = stats[:4].tolist()
-        if kl2_mean > self.log_n_samples:
-            self.lam = self.lam * self.lam_factor
-        else:
-            self.lam = self.lam / self.lam_factor
-        if kl2_max > self.log_n_samples + self.tolerance:
-            self.lam_max = self.lam_max * self.lam_factor
-        else:
-            self.lam_max = self.lam_max / self.lam_factor
-        self.lam_max = max(min(self.lam_max, self.lam_range[1]), 1.0)
-        if kl2_min < self.log_n_samples - self.tolerance:
-            self.lam_min = self.lam_min / self.lam_factor
-        else:
-            self.lam_min = self.lam_min * self.lam_factor
-        self.lam_min = max(min(self.lam_min, 1.0), self.lam_range[0])
+        self._update_lambdas(kl2_mean, kl2_min, kl2_max)
         info = {"kl_loss": kl_loss, "bits-mean": stats[1], "bits-min": stats[2], "bits-max": stats[3],
                 "lam": torch.zeros_like(stats[0]) + self.lam}
         return zhat, info
