@@ -106,6 +106,6 @@ struct gq_codebook {
     float *cb;        // [N,g] fp32 codebook
     float *nlpb;      // [N,g] fp32 beta*normal_log_prob (one rounding, as torch)
     __half *bimg;     // fp16 operand image, UMMA K-major no-swizzle core-matrix order
-    float *meta;      // device floats: [0]=max ||x||^2, [1]=max ||x||, [2..2+2g) per-column max |B|
+    float *meta;      // device floats: [0]=max ||x||^2, [1]=max ||x||, [2..2+2g) per-column max |B|, [2+2*kMaxG] their sum
     int device;
 };

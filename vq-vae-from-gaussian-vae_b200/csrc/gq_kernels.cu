@@ -223,7 +223,8 @@ int launch_quantize_exact(const gq_codebook *cb, const float *mu, const float *s
 //   bimg: fp16 [x^2 | x | 0-pad] rows of K = kpad, stored in UMMA K-major no-swizzle
 //   core-matrix order: byte(n,k) = (n/8)*(kpad/8)*128 + (k/8)*128 + (n%8)*16 + (k%8)*2.
 //   Rows n >= N (tile padding) are zero except k==2g slot... they are masked in the epilogue.
-//   meta[0] = max_n ||x_n||^2 , meta[1] = sqrt(meta[0]), meta[2+j] = max_n |B[n,j]|.
+//   meta[0] = max_n ||x_n||^2 , meta[1] = sqrt(meta[0]), meta[2+j] = max_n |B[n,j]|,
+//   meta[2+2*kMaxG] = sum_j meta[2+j].
 // ------------------------------------------------------------------------------------------
 __global__ void codebook_prep_kernel(const float *__restrict__ cb, const float *__restrict__ nlp_in,
                                      float *__restrict__ nlpb, __half *__restrict__ bimg,
@@ -265,19 +266,22 @@ __global__ void codebook_prep_kernel(const float *__restrict__ cb, const float *
     }
 }
 
-__global__ void codebook_meta_finish_kernel(float *meta)
+__global__ void codebook_meta_finish_kernel(float *meta, int g)
 {
     meta[1] = sqrtf(meta[0]) * 1.0000002f;
+    float s = 0.f;
+    for (int j = 0; j < 2 * g; ++j) s += meta[2 + j];
+    meta[2 + 2 * kMaxG] = s * 1.000001f;
 }
 
 int launch_codebook_prep(gq_codebook *cb, const float *nlp_in, cudaStream_t stream)
 {
-    cudaError_t e = cudaMemsetAsync(cb->meta, 0, sizeof(float) * (2 + 2 * kMaxG), stream);
+    cudaError_t e = cudaMemsetAsync(cb->meta, 0, sizeof(float) * (3 + 2 * kMaxG), stream);
     if (e != cudaSuccess) { set_error("memset meta: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
     int64_t blocks = (cb->n_pad + 255) / 256;
     codebook_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(cb->cb, nlp_in, cb->nlpb, cb->bimg, cb->meta,
                                                                cb->N, cb->n_pad, cb->g, cb->kpad, cb->beta);
-    codebook_meta_finish_kernel<<<1, 1, 0, stream>>>(cb->meta);
+    codebook_meta_finish_kernel<<<1, 1, 0, stream>>>(cb->meta, cb->g);
     count_launch(2);
     return check_launch("codebook_prep_kernel");
 }

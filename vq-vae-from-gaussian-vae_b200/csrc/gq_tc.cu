@@ -6,30 +6,35 @@
 // here it lives only in tensor memory.
 //
 // Pipeline (three launches + one optional fallback launch, all on the caller's stream):
-//   1. rows_prep_kernel   per row: A[r,:] = s_r*[beta/2 - 1/(2v) | mu/v] as fp16 in UMMA
-//                         core-matrix order, and a RIGOROUS window W_r bounding twice the
-//                         worst-case |fp16 tensor-core score - reference fp32 score| gap.
+//   1. rows_prep_kernel   per row: A[r,:] = s_r*[beta/2 - 1/(2v) | mu/v] as fp16, a RIGOROUS
+//                         window W_r bounding twice the worst-case |fp16 tensor-core score -
+//                         reference fp32 score| gap, and the (much smaller) margin of the fp32
+//                         prefilter used by the rescoring kernel.
 //   2. quantize_tc_kernel persistent, warp-specialised: bulk-async-copy (TMA engine) streams
 //                         the prepared [x^2 | x] codebook image through a shared-memory ring,
 //                         one thread issues tcgen05.mma (fp16 x fp16 -> fp32, M=128, N=128,
-//                         K=2g) into four TMEM accumulators, eight epilogue warps pull tiles
-//                         with tcgen05.ld (the whole 32x128 tile of a warp into registers, so
-//                         the TMEM stage is released before any math) and keep a running row
-//                         maximum with FMNMX3; a 32-column chunk whose maximum comes within
-//                         W_r of the running maximum is recorded as (max, chunk id).
+//                         K=2g) with the ROW operand resident in TENSOR MEMORY (so each MMA
+//                         reads only the codebook tile from shared memory) into three TMEM
+//                         accumulators, eight epilogue warps pull tiles with tcgen05.ld (the
+//                         whole 32x128 tile of a warp into registers, so the TMEM stage is
+//                         released before any math) and keep a running row maximum with
+//                         FMNMX3; a 32-column chunk whose maximum comes within W_r of the
+//                         running maximum is recorded as (max, chunk id).
 //   3. rescore_kernel     one warp per row: drop chunk records below (final max - W_r), score
-//                         the 32 codewords of every surviving chunk (lane = codeword) in the
-//                         reference's exact fp32 op order, first-max tie-break, write idx
-//                         (int64) and zhat.  Rows whose window is too wide, that overflow
-//                         their list, or that contain non-finite values go to
+//                         the 32 codewords of every surviving chunk (lane = codeword) with an
+//                         fp32 FMA form; if exactly one codeword lies within the prefilter
+//                         margin of the best it is the answer, otherwise the contenders are
+//                         re-scored in the reference's exact fp32 op order (first-max
+//                         tie-break).  Rows whose window is too wide, that overflow their
+//                         list, or that contain non-finite values go to
 //   4. quantize_exact_kernel (gq_kernels.cu) through a device-side row list.
 //
 // Why the result is exactly the reference argmax: with E_r >= |G~[n]/s - (S_ref[n] - Q_r)| for
 // all n (Q_r constant in n), the reference argmax n* satisfies
 // G~[n*] >= G~[m] - 2 s E_r for every m, in particular for the running maxima the epilogue
 // compares against (each is some G~[m]); so the chunk holding n* is always recorded (its maximum
-// is >= G~[n*]), survives the final filter, and n* wins the exact re-scoring of that chunk.
-// DESIGN.md ("error window") derives E_r.
+// is >= G~[n*]), survives the final filter, and n* survives the prefilter (same argument with
+// the prefilter's own bound) and wins the exact re-scoring.  DESIGN.md ("error window").
 #include "gq_common.cuh"
 #include "gq_internal.h"
 #include "gq_ptx.cuh"
@@ -68,9 +73,10 @@ using namespace gq::ptx;
 constexpr int kTileN = 128;          // codewords per B tile / MMA N
 constexpr int kBlockRows = 128;      // rows per MMA (M)
 constexpr int kUnitRows = 256;       // rows per CTA work unit (two row blocks)
-constexpr int kStages = 6;           // B ring depth
-constexpr int kAccStages = 2;        // TMEM accumulator stages per row block
-constexpr int kTmemCols = 512;       // 2 row blocks x 2 stages x 128 fp32 columns
+constexpr int kStages = 8;           // B ring depth
+constexpr int kAccStages = 3;        // TMEM accumulator stages, round-robin over (tile, row block)
+constexpr int kTmemCols = 512;       // 3 x 128 accumulator columns + the two A operands
+constexpr int kTmemACol = kAccStages * kTileN;
 constexpr int kThreads = 384;        // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;
 constexpr int kCap = 32;             // chunk records per (row, segment)
@@ -113,8 +119,9 @@ static TcPlan make_plan(const gq_codebook *cb, int64_t M)
 }
 
 struct TcWorkspace {
-    __half *a_img;      // [M_pad, kpad] fp16, core-matrix order
+    __half *a_img;      // [M_pad, kpad] fp16, row-major
     float *wrow;        // [M_pad] scaled window (negative => row goes to the exact fallback)
+    float *margin;      // [M_pad] prefilter margin (unscaled score units)
     SegHdr *seg;        // [M_pad, nseg]
     Cand *cand;         // [M_pad, nseg, kCap]
     uint32_t *fb_rows;  // [M] fallback row list
@@ -132,6 +139,8 @@ static TcWorkspace carve(const gq_codebook *cb, const TcPlan &p, void *base)
     w.a_img = reinterpret_cast<__half *>(ptr + off);
     off = align_up(off + p.M_pad * cb->kpad * 2, 256);
     w.wrow = reinterpret_cast<float *>(ptr + off);
+    off = align_up(off + p.M_pad * 4, 256);
+    w.margin = reinterpret_cast<float *>(ptr + off);
     off = align_up(off + p.M_pad * 4, 256);
     w.seg = reinterpret_cast<SegHdr *>(ptr + off);
     off = align_up(off + p.M_pad * p.nseg * (int64_t)sizeof(SegHdr), 256);
@@ -153,86 +162,115 @@ int64_t tc_workspace_bytes(const gq_codebook *cb, int64_t M)
 }
 
 // ---- 1. row preparation -----------------------------------------------------------------------
-// meta (from codebook prep): [0] = max_n ||x_n||^2, [1] = max_n ||x_n||, [2+j] = max_n |B[n,j]|.
+// meta (from codebook prep): [0] = max_n ||x_n||^2, [1] = max_n ||x_n||, [2+j] = max_n |B[n,j]|,
+// [2+2*kMaxG] = sum_j max_n |B[n,j]|.
 // Window (unscaled score units), all terms upper bounds:
 //   P     = min( sum_j |A_j| Bmax_j ,  max_k|a_k| * X2 + ||b||_2 * X1 )     >= sum_j |A_j B_nj|
 //   E_tc  = 1.01 * 2^-10 * P                    fp16 rounding of A and of B (2^-11 each), the
 //                                               product of both, fp32 tensor-core accumulation
 //         + 2^-25 * (sum_j Bmax_j / s + sum_j |A_j|)      fp16 subnormal floors
-//   E_ref = 2^-20 * sum_k[ (Xmax_k+|mu_k|)^2/(2 v_k) + |log std_k| + 2 + beta*X2max_k ]
+//         + 2^-22 * sum_k[(beta/2 + 1/(2v_k)) X2max_k + |b_k| Xmax_k]   A itself is evaluated in fp32
+//   E_ref = 2^-20 * R,  R = sum_k[ (Xmax_k+|mu_k|)^2/(2 v_k) + |log std_k| + 2 max(1,beta) + beta*X2max_k ]
 //                                               rounding of the reference's own fp32 evaluation
-//   W     = 2 * (E_tc + E_ref)
-// A is built in double so that its own error (2^-52) is irrelevant next to the fp16 rounding.
+//                                               (<= 7 roundings per term + <= 8 per summation path)
+//   W     = 2 * (E_tc + E_ref)                  (x 1.01: the bound itself is evaluated in fp32)
+//   E_pre = 3 * 2^-20 * R                       rounding of the rescoring kernel's fp32 FMA prefilter
+//   margin = 2 * (E_pre + E_ref) * 1.01         (E_ref, E_pre doubled for g = 32)
+template <int G, int KPAD>
+__device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G], const float (&ls)[G],
+                                         const float *__restrict__ meta, float beta, float w_max, bool valid,
+                                         __half *__restrict__ a_row, float *__restrict__ w_out,
+                                         float *__restrict__ margin_out)
+{
+    float A[2 * G];
+    bool bad = !valid;
+    float amax = 0.f, bnorm2 = 0.f, R = 0.f, p_naive = 0.f, maxA = 0.f, sumA = 0.f, eA = 0.f;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const float v = s[k] * s[k];
+        const float r = 0.5f / v;                  // 1/(2v)
+        const float a = 0.5f * beta - r;
+        const float b = m[k] / v;
+        A[k] = a;
+        A[G + k] = b;
+        const float x2m = meta[2 + k], xm = meta[2 + G + k];
+        amax = fmaxf(amax, fabsf(a));
+        bnorm2 = fmaf(b, b, bnorm2);
+        maxA = fmaxf(maxA, fmaxf(fabsf(a), fabsf(b)));
+        p_naive += fabsf(a) * x2m + fabsf(b) * xm;
+        sumA += fabsf(a) + fabsf(b);
+        eA += (0.5f * beta + r) * x2m + fabsf(b) * xm;
+        const float q = xm + fabsf(m[k]);
+        R += q * q * r + fabsf(ls[k]) + 2.0f * fmaxf(1.0f, beta) + beta * x2m;
+    }
+    if (!(maxA > 0.f) || !isfinite(maxA) || !isfinite(R) || !isfinite(bnorm2)) bad = true;
+    float scale = 1.f, w_scaled = -1.f, margin = 0.f;
+    if (!bad) {
+        int ex;
+        frexpf(maxA, &ex);               // maxA = f * 2^ex, f in [0.5, 1)
+        scale = ldexpf(1.0f, 8 - ex);    // max |A| * scale in [128, 256)
+        const float p_norm = amax * meta[0] + sqrtf(bnorm2) * 1.000001f * meta[1];
+        const float P = fminf(p_naive, p_norm);
+        const float sumB = meta[2 + 2 * kMaxG];
+        const float e_tc = 1.01f * ldexpf(P, -10) + ldexpf(sumB / scale + sumA, -25) + ldexpf(eA, -22);
+        constexpr float kE = (G > 16) ? 2.0f : 1.0f;   // deeper fp32 summation trees for g = 32
+        const float W = 2.02f * (e_tc + kE * ldexpf(R, -20));
+        margin = 2.02f * kE * 4.0f * ldexpf(R, -20);
+        if (!(W <= w_max) || !isfinite(W * scale)) bad = true;
+        else w_scaled = W * scale * 1.001f;
+    }
+    // fp16 row, 16-byte stores
+    uint4 *dst = reinterpret_cast<uint4 *>(a_row);
+#pragma unroll
+    for (int c = 0; c < KPAD / 8; ++c) {
+        __half2 h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k0 = c * 8 + 2 * i;
+            float v0 = 0.f, v1 = 0.f;
+            if (k0 < 2 * G) v0 = bad ? 0.f : A[k0 < 2 * G ? k0 : 0] * scale;
+            if (k0 + 1 < 2 * G) v1 = bad ? 0.f : A[k0 + 1 < 2 * G ? k0 + 1 : 0] * scale;
+            h[i] = __floats2half2_rn(v0, v1);
+        }
+        dst[c] = *reinterpret_cast<uint4 *>(h);
+    }
+    *w_out = w_scaled;
+    *margin_out = margin;
+}
+
 template <int G, int KPAD>
 __global__ void __launch_bounds__(128)
 rows_prep_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
                  const float *__restrict__ meta, __half *__restrict__ a_img, float *__restrict__ wrow,
-                 int64_t M, int64_t M_pad, float beta, float w_max)
+                 float *__restrict__ margin, int64_t M, int64_t M_pad, float beta, float w_max)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= M_pad) return;
-    constexpr int KCH = KPAD / 8;
-    char *rowbase = reinterpret_cast<char *>(a_img) + (r / 8) * (int64_t)KCH * 128 + (r % 8) * 16;
-    double A[2 * G];
-    bool bad = (r >= M);
-    double amax = 0.0, bnorm2 = 0.0, e_ref = 0.0, p_naive = 0.0, maxA = 0.0;
-    if (!bad) {
-        float m[G], s[G];
+    float m[G], s[G], ls[G];
+    const bool valid = r < M;
+    if (valid) {
         load_row<G>(mu + r * G, m);
         load_row<G>(std + r * G, s);
+        if (lstd) load_row<G>(lstd + r * G, ls);
+        else {
 #pragma unroll
-        for (int k = 0; k < G; ++k) {
-            double v = (double)s[k] * (double)s[k];
-            double a = 0.5 * (double)beta - 0.5 / v;
-            double b = (double)m[k] / v;
-            A[k] = a;
-            A[G + k] = b;
-            amax = fmax(amax, fabs(a));
-            bnorm2 += b * b;
-            maxA = fmax(maxA, fmax(fabs(a), fabs(b)));
-            double x2m = (double)meta[2 + k], xm = (double)meta[2 + G + k];
-            p_naive += fabs(a) * x2m + fabs(b) * xm;
-            double ls = lstd ? (double)lstd[r * G + k] : log((double)s[k]);
-            double q = (xm + fabs((double)m[k]));
-            e_ref += q * q / (2.0 * v) + fabs(ls) + 2.0 + (double)beta * x2m;
+            for (int k = 0; k < G; ++k) ls[k] = logf(s[k]);
         }
-        if (!(maxA > 0.0) || !isfinite(maxA) || !isfinite(e_ref)) bad = true;
-    }
-    double scale = 1.0;
-    float w_scaled = -1.0f;
-    if (!bad) {
-        int ex;
-        frexp(maxA, &ex);             // maxA = f * 2^ex, f in [0.5, 1)
-        scale = ldexp(1.0, 8 - ex);   // max |A| * scale in [128, 256)
-        double p_norm = amax * (double)meta[0] + sqrt(bnorm2) * (double)meta[1];
-        double P = fmin(p_naive, p_norm);
-        double sumB = 0.0, sumA = 0.0;
+    } else {
 #pragma unroll
-        for (int j = 0; j < 2 * G; ++j) { sumB += (double)meta[2 + j]; sumA += fabs(A[j]); }
-        double e_tc = 1.01 * ldexp(P, -10) + ldexp(sumB / scale + sumA, -25);
-        double W = 2.0 * (e_tc + ldexp(e_ref, -20));
-        if (!(W <= (double)w_max) || !isfinite(W * scale)) bad = true;
-        else w_scaled = (float)(W * scale * 1.001);
+        for (int k = 0; k < G; ++k) { m[k] = 0.f; s[k] = 1.f; ls[k] = 0.f; }
     }
-#pragma unroll
-    for (int k = 0; k < KPAD; ++k) {
-        float v = 0.f;
-        if (!bad && k < 2 * G) v = (float)(A[k] * scale);
-        *reinterpret_cast<__half *>(rowbase + (k / 8) * 128 + (k % 8) * 2) = __float2half_rn(v);
-    }
-    wrow[r] = w_scaled;
+    prep_row<G, KPAD>(m, s, ls, meta, beta, w_max, valid, a_img + r * KPAD, wrow + r, margin + r);
 }
 
 // ---- 2. the tensor-core search ------------------------------------------------------------------
 template <int KPAD>
 struct TcSmem {
     static constexpr int kBTileBytes = kTileN * KPAD * 2;
-    static constexpr int kABytes = kUnitRows * KPAD * 2;
     static constexpr int kBOff = 0;
-    static constexpr int kAOff = kBOff + kStages * kBTileBytes;
-    static constexpr int kBarOff = kAOff + 2 * kABytes;
-    // barriers: full_b[kStages], empty_b[kStages], a_full[2], a_empty[2], acc_full[4], acc_empty[4]
-    static constexpr int kNumBars = 2 * kStages + 4 + 8;
+    static constexpr int kBarOff = kBOff + kStages * kBTileBytes;
+    // barriers: full_b[kStages], empty_b[kStages], a_full[2], acc_full[3], acc_empty[3]
+    static constexpr int kNumBars = 2 * kStages + 2 + 2 * kAccStages;
     static constexpr int kSlotOff = kBarOff + kNumBars * 8;
     static constexpr int kBytes = kSlotOff + 16;
 };
@@ -252,10 +290,7 @@ __device__ __forceinline__ bool next_piece(int64_t &step, int64_t end, int tiles
     return true;
 }
 
-// Running-max epilogue for one chunk of 32 consecutive columns held in v[0..31].
-// Fast path: 16 FMNMX3/FMNMX and one compare.  Slow path (chunk maximum within the window of the
-// running maximum, ~10 times per row over 2048 chunks): raise the running max / threshold and
-// record (chunk max, chunk id); the rescoring kernel re-derives the candidates of the chunk.
+// Maximum of 32 consecutive columns: 14 FMNMX3 + 2 FMNMX.
 __device__ __forceinline__ float chunk_max32(const float *v)
 {
     float a0 = max3(v[0], v[1], v[2]), a1 = max3(v[3], v[4], v[5]), a2 = max3(v[6], v[7], v[8]);
@@ -266,12 +301,30 @@ __device__ __forceinline__ float chunk_max32(const float *v)
     return fmaxf(max3(b0, b1, b2), b3);
 }
 
+// Slow path (~10 times per row over 2048 chunks): raise the running max / threshold and record
+// (chunk max, chunk id); the rescoring kernel re-derives the candidates of the chunk.
 __device__ __forceinline__ void epi_record(float m, uint32_t chunk, float w, float &runmax, float &thr,
                                            uint32_t &cnt, Cand *__restrict__ list)
 {
     if (m > runmax) { runmax = m; thr = m - w; }
     if (cnt < (uint32_t)kCap) list[cnt] = Cand{m, chunk};
     ++cnt;
+}
+
+template <int KPAD>
+__device__ __forceinline__ void store_a_rows(uint32_t taddr, const __half *__restrict__ a_row)
+{
+    constexpr int NW = KPAD / 2;   // 32-bit words per row: two fp16 K-elements per TMEM column
+    uint32_t r[NW];
+#pragma unroll
+    for (int c = 0; c < NW / 4; ++c) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(a_row) + c);
+        r[4 * c + 0] = q.x; r[4 * c + 1] = q.y; r[4 * c + 2] = q.z; r[4 * c + 3] = q.w;
+    }
+    if constexpr (NW == 8) tmem_st_32x8(taddr, r);
+    else if constexpr (NW == 16) tmem_st_32x16(taddr, r);
+    else tmem_st_32x32(taddr, r);
+    tmem_st_wait();
 }
 
 template <int KPAD, bool DUMP>
@@ -283,15 +336,16 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 {
     using L = TcSmem<KPAD>;
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t smem_base = smem_u32(smem);
+    uint32_t smem_base;
+    // pin the shared-window base in a register (otherwise it is rematerialised from SR_CgaCtaId
+    // inside every wait loop)
+    asm volatile("mov.u32 %0, %1;" : "=r"(smem_base) : "r"(smem_u32(smem)));
     const uint32_t bar_base = smem_base + L::kBarOff;
-    // barrier addresses (shared-window u32), computed once
     auto full_b = [&](int i) { return bar_base + 8u * i; };
     auto empty_b = [&](int i) { return bar_base + 8u * (kStages + i); };
-    auto a_full = [&](int i) { return bar_base + 8u * (2 * kStages + i); };
-    auto a_empty = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };
-    auto acc_full = [&](int i) { return bar_base + 8u * (2 * kStages + 4 + i); };   // [rb*2 + stage]
-    auto acc_empty = [&](int i) { return bar_base + 8u * (2 * kStages + 8 + i); };
+    auto a_full = [&](int i) { return bar_base + 8u * (2 * kStages + i); };                      // per row block
+    auto acc_full = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };
+    auto acc_empty = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + kAccStages + i); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kSlotOff);
 
     const int warp = threadIdx.x >> 5;
@@ -302,9 +356,10 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 
     if (warp == 1 && lane == 0) {
         uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kBarOff);
-        for (int i = 0; i < 2 * kStages + 4; ++i) mbar_init(&bars[i], 1);           // full_b, empty_b, a_full, a_empty
-        for (int i = 0; i < 4; ++i) mbar_init(&bars[2 * kStages + 4 + i], 1);       // acc_full
-        for (int i = 0; i < 4; ++i) mbar_init(&bars[2 * kStages + 8 + i], 4);       // acc_empty: 4 epilogue warps
+        for (int i = 0; i < 2 * kStages; ++i) mbar_init(&bars[i], 1);                              // full_b, empty_b
+        for (int i = 0; i < 2; ++i) mbar_init(&bars[2 * kStages + i], 4);                          // a_full: 4 warps
+        for (int i = 0; i < kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + i], 1);             // acc_full
+        for (int i = 0; i < kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + kAccStages + i], 4);  // acc_empty
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -317,20 +372,13 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== producer: bulk async copies (TMA engine) =====
+        // ===== producer: bulk async copies (TMA engine) of codebook tiles =====
         if (lane == 0) {
             int64_t step = step_begin;
             Piece p;
             int stage = 0;
             uint32_t phase = 0;
-            int pi = 0;
             while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
-                const int ab = pi & 1;
-                mbar_wait_a(a_empty(ab), ((pi >> 1) & 1) ^ 1);
-                mbar_expect_tx_a(a_full(ab), L::kABytes);
-                bulk_g2s_a(smem_base + L::kAOff + ab * L::kABytes,
-                           reinterpret_cast<const char *>(a_img) + (int64_t)p.unit * L::kABytes, L::kABytes,
-                           a_full(ab));
                 for (int t = p.t0; t < p.t1; ++t) {
                     mbar_wait_a(empty_b(stage), phase ^ 1);
                     mbar_expect_tx_a(full_b(stage), L::kBTileBytes);
@@ -339,7 +387,6 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                                L::kBTileBytes, full_b(stage));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                ++pi;
             }
         }
     } else if (warp == 1) {
@@ -348,42 +395,39 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockRows, kTileN);
             constexpr uint32_t kLbo = 128;              // K-adjacent core matrices
             constexpr uint32_t kSbo = (KPAD / 8) * 128; // next 8-row group
-            const uint32_t a_base = smem_base + L::kAOff;
             const uint32_t b_base = smem_base + L::kBOff;
             int64_t step = step_begin;
             Piece p;
             int stage = 0;
             uint32_t phase = 0;
-            int as = 0;
+            int as = 0;          // accumulator stage of the next (tile, row block)
             uint32_t aphase = 0;
             int pi = 0;
             while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
-                const int ab = pi & 1;
-                mbar_wait_a(a_full(ab), (pi >> 1) & 1);
+                mbar_wait_a(a_full(0), pi & 1);
+                mbar_wait_a(a_full(1), pi & 1);
+                tc_fence_after();
                 for (int t = p.t0; t < p.t1; ++t) {
                     mbar_wait_a(full_b(stage), phase);
                     tc_fence_after();
+                    const uint32_t b_addr = b_base + stage * L::kBTileBytes;
 #pragma unroll
                     for (int rb = 0; rb < 2; ++rb) {
-                        mbar_wait_a(acc_empty(rb * 2 + as), aphase ^ 1);
+                        mbar_wait_a(acc_empty(as), aphase ^ 1);
                         tc_fence_after();
-                        const uint32_t d = tmem_base + (uint32_t)((rb * kAccStages + as) * kTileN);
-                        const uint32_t a_addr = a_base + ab * L::kABytes + rb * (kBlockRows * KPAD * 2);
-                        const uint32_t b_addr = b_base + stage * L::kBTileBytes;
+                        const uint32_t d = tmem_base + (uint32_t)(as * kTileN);
+                        const uint32_t a_t = tmem_base + (uint32_t)(kTmemACol + rb * (KPAD / 2));
 #pragma unroll
                         for (int j = 0; j < KPAD / 16; ++j) {
-                            uint64_t ad = umma_desc_kmajor_noswz(a_addr + j * 256, kLbo, kSbo);
                             uint64_t bd = umma_desc_kmajor_noswz(b_addr + j * 256, kLbo, kSbo);
-                            umma_f16_ss(d, ad, bd, idesc, j > 0 ? 1u : 0u);
+                            umma_f16_ts(d, a_t + j * 8, bd, idesc, j > 0 ? 1u : 0u);
                         }
-                        umma_commit_a(acc_full(rb * 2 + as));
+                        umma_commit_a(acc_full(as));
+                        if (++as == kAccStages) { as = 0; aphase ^= 1; }
                     }
                     umma_commit_a(empty_b(stage));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
-                    as ^= 1;
-                    if (as == 0) aphase ^= 1;
                 }
-                umma_commit_a(a_empty(ab));
                 ++pi;
             }
         }
@@ -392,31 +436,37 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         const int ew = warp - kEpiWarp0;
         const int rb = ew >> 2;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const bool padded = (N % kTileN) != 0;
         int64_t step = step_begin;
         Piece p;
-        int as = 0;
+        int as = rb;             // this row block consumes every other accumulator use
         uint32_t aphase = 0;
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
             const int64_t row = (int64_t)p.unit * kUnitRows + rb * kBlockRows + q * 32 + lane;
+            // Row operand into tensor memory.  Every MMA of the previous piece that read this row
+            // block's operand has completed: this warp consumed that piece's last accumulator.
+            store_a_rows<KPAD>(tmem_base + lane_base + (uint32_t)(kTmemACol + rb * (KPAD / 2)), a_img + row * KPAD);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(a_full(rb));
+
             const float w = wrow[row];
             float runmax = -CUDART_INF_F;
             float thr = (w >= 0.f) ? -CUDART_INF_F : CUDART_INF_F;
             uint32_t cnt = 0;
             Cand *list = cand + (row * nseg + p.seg) * (int64_t)kCap;
             for (int t = p.t0; t < p.t1; ++t) {
-                mbar_wait_a(acc_full(rb * 2 + as), aphase);
+                mbar_wait_a(acc_full(as), aphase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
-                                       (uint32_t)((rb * kAccStages + as) * kTileN);
                 float v[128];
-                tmem_ld_32x128_sync(taddr, v);
+                tmem_ld_32x128_sync(tmem_base + lane_base + (uint32_t)(as * kTileN), v);
                 // the tile now lives in registers: hand the TMEM stage back before doing any math
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_a(acc_empty(rb * 2 + as));
-                as ^= 1;
-                if (as == 0) aphase ^= 1;
+                if (lane == 0) mbar_arrive_a(acc_empty(as));
+                as += 2;
+                if (as >= kAccStages) { as -= kAccStages; aphase ^= 1; }
 
                 if constexpr (DUMP) {
                     // debug build only: spill the raw tensor-core scores [M_pad, tiles*128]
@@ -457,28 +507,45 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     }
 }
 
-// ---- 3. exact re-scoring of the recorded chunks: one warp per row, lane = codeword -----------------
-constexpr int kRescoreWarps = 4;
+// ---- 3. re-scoring of the recorded chunks: one warp per row, lane = codeword ----------------------
+constexpr int kRescoreWarps = 8;
+
+template <int G>
+__device__ __forceinline__ float prefilter_score(const float (&x)[G], const float (&m)[G], const float (&ri)[G],
+                                                 float hb)
+{
+    float a2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const float d = x[k] - m[k];
+        a2 = fmaf(-d * d, ri[k], a2);
+        a2 = fmaf(hb * x[k], x[k], a2);
+    }
+    return a2;
+}
 
 template <int G>
 __global__ void __launch_bounds__(kRescoreWarps * 32)
 rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
                const float *__restrict__ cb, const float *__restrict__ nlpb, const float *__restrict__ wrow,
-               const SegHdr *__restrict__ seg_hdr, const Cand *__restrict__ cand, int64_t M, int64_t N, int tiles,
-               int steps_per_cta, int nseg, int64_t *__restrict__ idx_out, float *__restrict__ zhat_out,
+               const float *__restrict__ margin_row, const SegHdr *__restrict__ seg_hdr,
+               const Cand *__restrict__ cand, int64_t M, int64_t N, int tiles, int steps_per_cta, int nseg,
+               float beta, int64_t *__restrict__ idx_out, float *__restrict__ zhat_out,
                uint32_t *__restrict__ fb_rows, uint32_t *__restrict__ fb_count, uint32_t *__restrict__ stats)
 {
+    __shared__ float s_par[kRescoreWarps][4][G];   // mu, den, log std, 1/den of the warp's row
     const int lane = threadIdx.x & 31;
-    const int64_t warp_global = (int64_t)blockIdx.x * kRescoreWarps + (threadIdx.x >> 5);
+    const int wib = threadIdx.x >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * kRescoreWarps + wib;
     const int64_t nwarps = (int64_t)gridDim.x * kRescoreWarps;
-    uint32_t st_rows = 0, st_resc = 0, st_fb = 0, st_ovf = 0;
+    const float hb = 0.5f * beta;
+    uint32_t st_rows = 0, st_pre = 0, st_exact = 0, st_fb = 0, st_ovf = 0;
 
     for (int64_t r = warp_global; r < M; r += nwarps) {
         const float w = wrow[r];
         bool fallback = !(w >= 0.f);
         bool overflow = false;
         int best_idx = 0x7fffffff;
-        float best = -CUDART_INF_F;
         if (!fallback) {
             const int unit = (int)(r / kUnitRows);
             const int64_t s0 = (int64_t)unit * tiles;
@@ -494,17 +561,24 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
             if (overflow || !(gmax > -CUDART_INF_F)) fallback = true;
             else {
                 const float thr = gmax - w;
-                float m[G], den[G], ls[G];
-                load_row<G>(mu + r * G, m);
-                {
-                    float sd[G];
-                    load_row<G>(std + r * G, sd);
-#pragma unroll
-                    for (int k = 0; k < G; ++k) {
-                        den[k] = __fmul_rn(2.0f, __fmul_rn(sd[k], sd[k]));
-                        ls[k] = lstd ? __ldg(lstd + r * G + k) : logf(sd[k]);
-                    }
+                const float margin = margin_row[r];
+                __syncwarp();
+                if (lane < G) {
+                    const float sd = __ldg(std + r * G + lane);
+                    const float dn = __fmul_rn(2.0f, __fmul_rn(sd, sd));
+                    s_par[wib][0][lane] = __ldg(mu + r * G + lane);
+                    s_par[wib][1][lane] = dn;
+                    s_par[wib][2][lane] = lstd ? __ldg(lstd + r * G + lane) : logf(sd);
+                    s_par[wib][3][lane] = 1.0f / dn;
                 }
+                __syncwarp();
+                float m[G], ri[G];
+#pragma unroll
+                for (int k = 0; k < G; ++k) { m[k] = s_par[wib][0][k]; ri[k] = s_par[wib][3][k]; }
+
+                // pass 1: fp32 FMA prefilter, per-lane best and runner-up
+                float a_best = -CUDART_INF_F, a_second = -CUDART_INF_F;
+                int n_best = 0x7fffffff;
                 for (int s = 0; s < npieces; ++s) {
                     const uint32_t cnt = seg_hdr[r * nseg + s].cnt;
                     const Cand *list = cand + (r * nseg + s) * (int64_t)kCap;
@@ -512,23 +586,61 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                         const Cand c = list[i];            // warp-uniform
                         if (!(c.score >= thr)) continue;
                         const int64_t n = (int64_t)c.idx * kChunk + lane;
-                        st_resc += 1;
+                        st_pre += 1;
                         if (n < N) {
-                            float x[G], nb[G];
+                            float x[G];
                             load_row<G>(cb + n * G, x);
-                            load_row<G>(nlpb + n * G, nb);
-                            const float sc = score_exact<G>(x, nb, m, den, ls);
-                            if (sc > best || (sc == best && (int)n < best_idx)) { best = sc; best_idx = (int)n; }
+                            const float a2 = prefilter_score<G>(x, m, ri, hb);
+                            if (a2 > a_best) { a_second = a_best; a_best = a2; n_best = (int)n; }
+                            else if (a2 > a_second) a_second = a2;
                         }
                     }
                 }
+                float g2 = a_best;
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
-                    if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+                for (int off = 16; off > 0; off >>= 1) g2 = fmaxf(g2, __shfl_xor_sync(0xffffffffu, g2, off));
+                const float lim = g2 - margin;
+                const unsigned firsts = __ballot_sync(0xffffffffu, a_best >= lim);
+                const unsigned seconds = __ballot_sync(0xffffffffu, a_second >= lim);
+                if (!(g2 > -CUDART_INF_F) || !(margin >= 0.f) || firsts == 0u) {
+                    fallback = true;   // NaN / -inf rows: let the scan decide
+                } else if (__popc(firsts) == 1 && seconds == 0u) {
+                    best_idx = __shfl_sync(0xffffffffu, n_best, __ffs(firsts) - 1);
+                } else {
+                    // several codewords within the prefilter margin: settle them in the exact op order
+                    st_exact += 1;
+                    float den[G], ls[G];
+#pragma unroll
+                    for (int k = 0; k < G; ++k) { den[k] = s_par[wib][1][k]; ls[k] = s_par[wib][2][k]; }
+                    float best = -CUDART_INF_F;
+                    for (int s = 0; s < npieces; ++s) {
+                        const uint32_t cnt = seg_hdr[r * nseg + s].cnt;
+                        const Cand *list = cand + (r * nseg + s) * (int64_t)kCap;
+                        for (uint32_t i = 0; i < cnt; ++i) {
+                            const Cand c = list[i];
+                            if (!(c.score >= thr)) continue;
+                            const int64_t n = (int64_t)c.idx * kChunk + lane;
+                            if (n < N) {
+                                float x[G];
+                                load_row<G>(cb + n * G, x);
+                                const float a2 = prefilter_score<G>(x, m, ri, hb);
+                                if (a2 >= lim) {
+                                    float nb[G];
+                                    load_row<G>(nlpb + n * G, nb);
+                                    const float sc = score_exact<G>(x, nb, m, den, ls);
+                                    if (sc > best || (sc == best && (int)n < best_idx)) { best = sc; best_idx = (int)n; }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
+                        if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+                    }
+                    if (best_idx == 0x7fffffff || !(best > -CUDART_INF_F)) fallback = true;
                 }
-                if (best_idx == 0x7fffffff || !(best > -CUDART_INF_F)) fallback = true;  // NaN / -inf rows: let the scan decide
             }
         }
         if (fallback) {
@@ -546,9 +658,10 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
     }
     if (stats && lane == 0) {
         atomicAdd(&stats[0], st_rows);
-        atomicAdd(&stats[1], st_resc * 32u);
+        atomicAdd(&stats[1], st_pre * 32u);
         atomicAdd(&stats[2], st_fb);
         atomicAdd(&stats[3], st_ovf);
+        atomicAdd(&stats[4], st_exact);
     }
 }
 
@@ -570,7 +683,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
     if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
 
     rows_prep_kernel<G, KPAD><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
-        mu, std, lstd, cb->meta, w.a_img, w.wrow, M, p.M_pad, cb->beta, w_max);
+        mu, std, lstd, cb->meta, w.a_img, w.wrow, w.margin, M, p.M_pad, cb->beta, w_max);
     int rc = check_launch("rows_prep_kernel");
     if (rc) return rc;
 
@@ -591,10 +704,10 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
 
     {
         int64_t need = (M + kRescoreWarps - 1) / kRescoreWarps;
-        int blocks = (int)imin(need, (int64_t)device_sm_count() * 16);
+        int blocks = (int)imin(need, (int64_t)device_sm_count() * 8);
         rescore_kernel<G><<<blocks, kRescoreWarps * 32, 0, stream>>>(
-            mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.seg, w.cand, M, cb->N, p.tiles, p.steps_per_cta, p.nseg, idx,
-            zhat, w.fb_rows, w.counters, stats);
+            mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.margin, w.seg, w.cand, M, cb->N, p.tiles, p.steps_per_cta,
+            p.nseg, cb->beta, idx, zhat, w.fb_rows, w.counters, stats);
     }
     rc = check_launch("rescore_kernel");
     if (rc) return rc;
@@ -617,7 +730,7 @@ static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std,
                                          L::kBytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
     rows_prep_kernel<G, KPAD><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
-        mu, std, lstd, cb->meta, w.a_img, w.wrow, M, p.M_pad, cb->beta, w_max);
+        mu, std, lstd, cb->meta, w.a_img, w.wrow, w.margin, M, p.M_pad, cb->beta, w_max);
     int rc = check_launch("rows_prep_kernel");
     if (rc) return rc;
     quantize_tc_kernel<KPAD, true><<<p.ctas, kThreads, L::kBytes, stream>>>(
@@ -676,7 +789,7 @@ int debug_tc_scores(const gq_codebook *cb, const float *mu, const float *std, co
     }
 }
 
-// Host-only: the stream-K decomposition for (N, g, M) on `sms` SMs, for CPU-side tests.
+// Host-only: the stream-K decomposition for (N, M) on `sms` SMs, for CPU-side tests.
 // out[0..5] = {units, tiles, ctas, steps_per_cta, nseg, M_pad}
 void debug_plan(int64_t N, int64_t M, int sms, int64_t *out)
 {
