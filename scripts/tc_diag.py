@@ -160,7 +160,7 @@ if __name__ == "__main__":
     for name in names:
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, __file__, "--stage", name], capture_output=True, text=True, timeout=240)
+            p = subprocess.run([sys.executable, __file__, "--stage", name], capture_output=True, text=True, timeout=75)
             tail = (p.stdout[-1500:] + p.stderr[-1500:]).strip()
             print(f"[{name}] rc={p.returncode} {time.time() - t0:.1f}s\n{tail}\n", flush=True)
         except subprocess.TimeoutExpired:

@@ -77,7 +77,7 @@ constexpr int kStages = 8;           // B ring depth
 constexpr int kAccStages = 3;        // TMEM accumulator stages, round-robin over (tile, row block)
 constexpr int kTmemCols = 512;       // 3 x 128 accumulator columns + the two A operands
 constexpr int kTmemACol = kAccStages * kTileN;
-constexpr int kThreads = 384;        // 4 control warps + 8 epilogue warps
+constexpr int kThreads = 384;        // producer, 2 MMA issuers, TMEM allocator + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;
 constexpr int kCap = 32;             // chunk records per (row, segment)
 constexpr int kChunk = 32;           // columns per recorded chunk
@@ -269,8 +269,8 @@ struct TcSmem {
     static constexpr int kBTileBytes = kTileN * KPAD * 2;
     static constexpr int kBOff = 0;
     static constexpr int kBarOff = kBOff + kStages * kBTileBytes;
-    // barriers: full_b[kStages], empty_b[kStages], a_full[2], acc_full[3], acc_empty[3]
-    static constexpr int kNumBars = 2 * kStages + 2 + 2 * kAccStages;
+    // barriers: full_b[kStages], empty_b[kStages], a_full[2], acc_full[3][2], acc_empty[3][2]
+    static constexpr int kNumBars = 2 * kStages + 2 + 4 * kAccStages;
     static constexpr int kSlotOff = kBarOff + kNumBars * 8;
     static constexpr int kBytes = kSlotOff + 16;
 };
@@ -344,8 +344,12 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     auto full_b = [&](int i) { return bar_base + 8u * i; };
     auto empty_b = [&](int i) { return bar_base + 8u * (kStages + i); };
     auto a_full = [&](int i) { return bar_base + 8u * (2 * kStages + i); };                      // per row block
-    auto acc_full = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };
-    auto acc_empty = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + kAccStages + i); };
+    // Accumulator barriers are per (stage, row block): the three stages are shared round-robin by
+    // the two row blocks, so a per-stage barrier would be waited on by each party only every other
+    // phase, which a parity wait cannot tell apart.  acc_full(s, rb): MMA of row block rb into stage
+    // s complete.  acc_empty(s, rb): the epilogue warps of row block rb have drained stage s.
+    auto acc_full = [&](int st, int rb_) { return bar_base + 8u * (2 * kStages + 2 + 2 * st + rb_); };
+    auto acc_empty = [&](int st, int rb_) { return bar_base + 8u * (2 * kStages + 2 + 2 * kAccStages + 2 * st + rb_); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kSlotOff);
 
     const int warp = threadIdx.x >> 5;
@@ -356,10 +360,11 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 
     if (warp == 1 && lane == 0) {
         uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kBarOff);
-        for (int i = 0; i < 2 * kStages; ++i) mbar_init(&bars[i], 1);                              // full_b, empty_b
+        for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);                                  // full_b
+        for (int i = 0; i < kStages; ++i) mbar_init(&bars[kStages + i], 2);                        // empty_b: 2 issuers
         for (int i = 0; i < 2; ++i) mbar_init(&bars[2 * kStages + i], 4);                          // a_full: 4 warps
-        for (int i = 0; i < kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + i], 1);             // acc_full
-        for (int i = 0; i < kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + kAccStages + i], 4);  // acc_empty
+        for (int i = 0; i < 2 * kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + i], 1);                   // acc_full
+        for (int i = 0; i < 2 * kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + 2 * kAccStages + i], 4);  // acc_empty
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -373,63 +378,73 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 
     if (warp == 0) {
         // ===== producer: bulk async copies (TMA engine) of codebook tiles =====
-        if (lane == 0) {
-            int64_t step = step_begin;
-            Piece p;
-            int stage = 0;
-            uint32_t phase = 0;
-            while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
-                for (int t = p.t0; t < p.t1; ++t) {
-                    mbar_wait_a(empty_b(stage), phase ^ 1);
+        // The whole warp runs the loop (warp-uniform control flow keeps addresses on the uniform
+        // datapath); one elected lane arms the barrier and issues the copy.
+        int64_t step = step_begin;
+        Piece p;
+        int stage = 0;
+        uint32_t phase = 0;
+        while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
+            for (int t = p.t0; t < p.t1; ++t) {
+                mbar_wait_a(empty_b(stage), phase ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx_a(full_b(stage), L::kBTileBytes);
                     bulk_g2s_a(smem_base + L::kBOff + stage * L::kBTileBytes,
                                reinterpret_cast<const char *>(b_img) + (int64_t)t * L::kBTileBytes,
                                L::kBTileBytes, full_b(stage));
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: one thread drives the tensor core =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockRows, kTileN);
-            constexpr uint32_t kLbo = 128;              // K-adjacent core matrices
-            constexpr uint32_t kSbo = (KPAD / 8) * 128; // next 8-row group
-            const uint32_t b_base = smem_base + L::kBOff;
-            int64_t step = step_begin;
-            Piece p;
-            int stage = 0;
-            uint32_t phase = 0;
-            int as = 0;          // accumulator stage of the next (tile, row block)
-            uint32_t aphase = 0;
-            int pi = 0;
-            while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
-                mbar_wait_a(a_full(0), pi & 1);
-                mbar_wait_a(a_full(1), pi & 1);
+    } else if (warp == 1 || warp == 3) {
+        // ===== MMA issuers: warp 1 drives row block 0, warp 3 row block 1.  Each warp waits
+        // together (warp-uniform control flow), one elected lane issues to the tensor core. =====
+        const int rb = warp >> 1;
+        constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockRows, kTileN);
+        constexpr uint32_t kLbo = 128;              // K-adjacent core matrices
+        constexpr uint32_t kSbo = (KPAD / 8) * 128; // next 8-row group
+        // descriptor words: everything but the 14-bit start address is loop invariant
+        constexpr uint32_t desc_hi = ((kSbo >> 4) & 0x3FFFu) | (1u << 14);           // SBO, version = 1
+        const uint32_t desc_lo0 = (((smem_base + L::kBOff) >> 4) & 0x3FFFu) | (((kLbo >> 4) & 0x3FFFu) << 16);
+        const uint32_t a_t = tmem_base + (uint32_t)(kTmemACol + rb * (KPAD / 2));
+        int64_t step = step_begin;
+        Piece p;
+        int stage = 0;
+        uint32_t phase = 0;
+        // Use q = 2*i + rb of the accumulator ring goes to stage q % 3; this row block's i-th use is
+        // its (i/3)-th visit of that stage (cycle parity cp).  The stage was last drained by the
+        // OTHER row block (use q-3); that is its (i/3)-th drain of the stage if the other row block
+        // is the stage's first user (stage parity != rb), else its (i/3 - 1)-th.
+        int as = rb;         // stage of the next use
+        uint32_t cp = 0;     // parity of i / 3
+        int pos = 0;         // i % 3
+        int pi = 0;
+        while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
+            mbar_wait_a(a_full(rb), pi & 1);
+            tc_fence_after();
+            for (int t = p.t0; t < p.t1; ++t) {
+                const uint32_t empty_par = ((as & 1) == rb) ? (cp ^ 1) : cp;
+                mbar_wait2_a(full_b(stage), phase, acc_empty(as, rb ^ 1), empty_par);
                 tc_fence_after();
-                for (int t = p.t0; t < p.t1; ++t) {
-                    mbar_wait_a(full_b(stage), phase);
-                    tc_fence_after();
-                    const uint32_t b_addr = b_base + stage * L::kBTileBytes;
+                if (elect_one()) {
+                    const uint32_t d = tmem_base + (uint32_t)(as * kTileN);
+                    const uint32_t desc_lo = desc_lo0 + (uint32_t)stage * (L::kBTileBytes >> 4);
 #pragma unroll
-                    for (int rb = 0; rb < 2; ++rb) {
-                        mbar_wait_a(acc_empty(as), aphase ^ 1);
-                        tc_fence_after();
-                        const uint32_t d = tmem_base + (uint32_t)(as * kTileN);
-                        const uint32_t a_t = tmem_base + (uint32_t)(kTmemACol + rb * (KPAD / 2));
-#pragma unroll
-                        for (int j = 0; j < KPAD / 16; ++j) {
-                            uint64_t bd = umma_desc_kmajor_noswz(b_addr + j * 256, kLbo, kSbo);
-                            umma_f16_ts(d, a_t + j * 8, bd, idesc, j > 0 ? 1u : 0u);
-                        }
-                        umma_commit_a(acc_full(as));
-                        if (++as == kAccStages) { as = 0; aphase ^= 1; }
+                    for (int j = 0; j < KPAD / 16; ++j) {
+                        const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo + j * 16);
+                        umma_f16_ts(d, a_t + j * 8, bd, idesc, j > 0 ? 1u : 0u);
                     }
-                    umma_commit_a(empty_b(stage));
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    umma_commit_a(acc_full(as, rb));
+                    umma_commit_a(empty_b(stage));   // 2 arrivals (one per row block) free the B slot
                 }
-                ++pi;
+                __syncwarp();
+                as += 2;
+                if (as >= kAccStages) as -= kAccStages;
+                if (++pos == 3) { pos = 0; cp ^= 1; }
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            ++pi;
         }
     } else if (warp >= kEpiWarp0) {
         // ===== epilogue: TMEM -> registers, running row max, chunk records =====
@@ -441,7 +456,8 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         int64_t step = step_begin;
         Piece p;
         int as = rb;             // this row block consumes every other accumulator use
-        uint32_t aphase = 0;
+        uint32_t cp = 0;         // parity of (own use index / 3) == phase parity of acc_full(as, rb)
+        int pos = 0;
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
             const int64_t row = (int64_t)p.unit * kUnitRows + rb * kBlockRows + q * 32 + lane;
             // Row operand into tensor memory.  Every MMA of the previous piece that read this row
@@ -457,16 +473,17 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             uint32_t cnt = 0;
             Cand *list = cand + (row * nseg + p.seg) * (int64_t)kCap;
             for (int t = p.t0; t < p.t1; ++t) {
-                mbar_wait_a(acc_full(as), aphase);
+                mbar_wait_a(acc_full(as, rb), cp);
                 tc_fence_after();
                 float v[128];
                 tmem_ld_32x128_sync(tmem_base + lane_base + (uint32_t)(as * kTileN), v);
                 // the tile now lives in registers: hand the TMEM stage back before doing any math
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_a(acc_empty(as));
+                if (lane == 0) mbar_arrive_a(acc_empty(as, rb));
                 as += 2;
-                if (as >= kAccStages) { as -= kAccStages; aphase ^= 1; }
+                if (as >= kAccStages) as -= kAccStages;
+                if (++pos == 3) { pos = 0; cp ^= 1; }
 
                 if constexpr (DUMP) {
                     // debug build only: spill the raw tensor-core scores [M_pad, tiles*128]
@@ -524,8 +541,54 @@ __device__ __forceinline__ float prefilter_score(const float (&x)[G], const floa
     return a2;
 }
 
+// Rare path of the rescoring kernel (a few percent of rows): several codewords lie within the
+// prefilter margin of the best one; settle them in the reference's exact fp32 op order.  Kept out of
+// line so that its register needs do not lower the occupancy of the common path.
 template <int G>
-__global__ void __launch_bounds__(kRescoreWarps * 32)
+__device__ __noinline__ int settle_exact(const float *__restrict__ par /* [4][G] smem: mu, den, lstd, 1/den */,
+                                         const float *__restrict__ cb, const float *__restrict__ nlpb,
+                                         const SegHdr *__restrict__ seg_row, const Cand *__restrict__ cand_row,
+                                         int npieces, int64_t N, float thr, float lim, float hb, int lane)
+{
+    float m[G], den[G], ls[G], ri[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) { m[k] = par[k]; den[k] = par[G + k]; ls[k] = par[2 * G + k]; ri[k] = par[3 * G + k]; }
+    float best = -CUDART_INF_F;
+    int best_idx = 0x7fffffff;
+    for (int s = 0; s < npieces; ++s) {
+        const SegHdr h = seg_row[s];
+        const Cand c = cand_row[(int64_t)s * kCap + lane];
+        unsigned surv = __ballot_sync(0xffffffffu, (uint32_t)lane < h.cnt && c.score >= thr);
+        while (surv) {
+            const int i = __ffs(surv) - 1;
+            surv &= surv - 1;
+            const uint32_t chunk = __shfl_sync(0xffffffffu, c.idx, i);
+            const int64_t n = (int64_t)chunk * kChunk + lane;
+            if (n < N) {
+                float x[G];
+                load_row<G>(cb + n * G, x);
+                const float a2 = prefilter_score<G>(x, m, ri, hb);
+                if (a2 >= lim) {
+                    float nb[G];
+                    load_row<G>(nlpb + n * G, nb);
+                    const float sc = score_exact<G>(x, nb, m, den, ls);
+                    if (sc > best || (sc == best && (int)n < best_idx)) { best = sc; best_idx = (int)n; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
+        if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+    }
+    if (!(best > -CUDART_INF_F)) best_idx = 0x7fffffff;
+    return best_idx;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kRescoreWarps * 32, (G <= 16) ? 3 : 1)
 rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
                const float *__restrict__ cb, const float *__restrict__ nlpb, const float *__restrict__ wrow,
                const float *__restrict__ margin_row, const SegHdr *__restrict__ seg_hdr,
@@ -540,6 +603,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
     const int64_t nwarps = (int64_t)gridDim.x * kRescoreWarps;
     const float hb = 0.5f * beta;
     uint32_t st_rows = 0, st_pre = 0, st_exact = 0, st_fb = 0, st_ovf = 0;
+    constexpr int kFast = 2;   // segments whose headers + records are fetched in one round of loads
 
     for (int64_t r = warp_global; r < M; r += nwarps) {
         const float w = wrow[r];
@@ -552,40 +616,58 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
             const int first = (int)(s0 / steps_per_cta);
             const int last = (int)((s0 + tiles - 1) / steps_per_cta);
             const int npieces = last - first + 1;
+            // one round of independent loads: headers and (speculatively, all kCap slots) records of the
+            // first kFast segments, lane i taking record i; slots >= cnt are ignored below
+            SegHdr hd[kFast];
+            Cand rec[kFast];
+#pragma unroll
+            for (int s = 0; s < kFast; ++s) {
+                hd[s] = SegHdr{-CUDART_INF_F, 0u};
+                rec[s] = Cand{-CUDART_INF_F, 0u};
+                if (s < npieces) {
+                    hd[s] = seg_hdr[r * nseg + s];
+                    rec[s] = cand[(r * nseg + s) * (int64_t)kCap + lane];
+                }
+            }
+            const float margin = margin_row[r];
+            __syncwarp();
+            if (lane < G) {
+                const float sd = __ldg(std + r * G + lane);
+                const float dn = __fmul_rn(2.0f, __fmul_rn(sd, sd));
+                s_par[wib][0][lane] = __ldg(mu + r * G + lane);
+                s_par[wib][1][lane] = dn;
+                s_par[wib][2][lane] = lstd ? __ldg(lstd + r * G + lane) : logf(sd);
+                s_par[wib][3][lane] = 1.0f / dn;
+            }
             float gmax = -CUDART_INF_F;
-            for (int s = 0; s < npieces; ++s) {
+#pragma unroll
+            for (int s = 0; s < kFast; ++s) {
+                gmax = fmaxf(gmax, hd[s].runmax);
+                if (hd[s].cnt > (uint32_t)kCap) overflow = true;
+            }
+            for (int s = kFast; s < npieces; ++s) {
                 SegHdr h = seg_hdr[r * nseg + s];
                 gmax = fmaxf(gmax, h.runmax);
                 if (h.cnt > (uint32_t)kCap) overflow = true;
             }
+            __syncwarp();
             if (overflow || !(gmax > -CUDART_INF_F)) fallback = true;
             else {
                 const float thr = gmax - w;
-                const float margin = margin_row[r];
-                __syncwarp();
-                if (lane < G) {
-                    const float sd = __ldg(std + r * G + lane);
-                    const float dn = __fmul_rn(2.0f, __fmul_rn(sd, sd));
-                    s_par[wib][0][lane] = __ldg(mu + r * G + lane);
-                    s_par[wib][1][lane] = dn;
-                    s_par[wib][2][lane] = lstd ? __ldg(lstd + r * G + lane) : logf(sd);
-                    s_par[wib][3][lane] = 1.0f / dn;
-                }
-                __syncwarp();
                 float m[G], ri[G];
 #pragma unroll
                 for (int k = 0; k < G; ++k) { m[k] = s_par[wib][0][k]; ri[k] = s_par[wib][3][k]; }
 
-                // pass 1: fp32 FMA prefilter, per-lane best and runner-up
+                // pass 1: fp32 FMA prefilter over the surviving chunks, per-lane best and runner-up
                 float a_best = -CUDART_INF_F, a_second = -CUDART_INF_F;
                 int n_best = 0x7fffffff;
-                for (int s = 0; s < npieces; ++s) {
-                    const uint32_t cnt = seg_hdr[r * nseg + s].cnt;
-                    const Cand *list = cand + (r * nseg + s) * (int64_t)kCap;
-                    for (uint32_t i = 0; i < cnt; ++i) {
-                        const Cand c = list[i];            // warp-uniform
-                        if (!(c.score >= thr)) continue;
-                        const int64_t n = (int64_t)c.idx * kChunk + lane;
+                auto scan = [&](uint32_t cnt, const Cand &c) {
+                    unsigned surv = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && c.score >= thr);
+                    while (surv) {
+                        const int i = __ffs(surv) - 1;
+                        surv &= surv - 1;
+                        const uint32_t chunk = __shfl_sync(0xffffffffu, c.idx, i);
+                        const int64_t n = (int64_t)chunk * kChunk + lane;
                         st_pre += 1;
                         if (n < N) {
                             float x[G];
@@ -595,6 +677,13 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                             else if (a2 > a_second) a_second = a2;
                         }
                     }
+                };
+#pragma unroll
+                for (int s = 0; s < kFast; ++s) scan(hd[s].cnt, rec[s]);
+                for (int s = kFast; s < npieces; ++s) {
+                    const SegHdr h = seg_hdr[r * nseg + s];
+                    const Cand c = cand[(r * nseg + s) * (int64_t)kCap + lane];
+                    scan(h.cnt, c);
                 }
                 float g2 = a_best;
 #pragma unroll
@@ -609,37 +698,9 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                 } else {
                     // several codewords within the prefilter margin: settle them in the exact op order
                     st_exact += 1;
-                    float den[G], ls[G];
-#pragma unroll
-                    for (int k = 0; k < G; ++k) { den[k] = s_par[wib][1][k]; ls[k] = s_par[wib][2][k]; }
-                    float best = -CUDART_INF_F;
-                    for (int s = 0; s < npieces; ++s) {
-                        const uint32_t cnt = seg_hdr[r * nseg + s].cnt;
-                        const Cand *list = cand + (r * nseg + s) * (int64_t)kCap;
-                        for (uint32_t i = 0; i < cnt; ++i) {
-                            const Cand c = list[i];
-                            if (!(c.score >= thr)) continue;
-                            const int64_t n = (int64_t)c.idx * kChunk + lane;
-                            if (n < N) {
-                                float x[G];
-                                load_row<G>(cb + n * G, x);
-                                const float a2 = prefilter_score<G>(x, m, ri, hb);
-                                if (a2 >= lim) {
-                                    float nb[G];
-                                    load_row<G>(nlpb + n * G, nb);
-                                    const float sc = score_exact<G>(x, nb, m, den, ls);
-                                    if (sc > best || (sc == best && (int)n < best_idx)) { best = sc; best_idx = (int)n; }
-                                }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-                        const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
-                        if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
-                    }
-                    if (best_idx == 0x7fffffff || !(best > -CUDART_INF_F)) fallback = true;
+                    best_idx = settle_exact<G>(&s_par[wib][0][0], cb, nlpb, seg_hdr + r * nseg,
+                                               cand + r * nseg * (int64_t)kCap, npieces, N, thr, lim, hb, lane);
+                    if (best_idx == 0x7fffffff) fallback = true;
                 }
             }
         }
