@@ -92,6 +92,20 @@ int gq_quantize_exact(const gq_codebook_t *cb, const float *mu, const float *std
                       const float *log_std, int64_t M, int64_t *idx, float *zhat,
                       gq_stream_t stream);
 
+/* ---- fused eval branch from the raw latent ----------------------------------------------
+ * The whole eval branch of GaussianQuantRegularizer.forward (gaussian.py:62-80,121-159) in one
+ * call: z fp32 [b,l,2C] (BLC) or [b,2C,h,w] (BCHW, l = h*w) -> idx int64 [b,l,ncb] / [b,ncb,h,w],
+ * zhat fp32 [b,l,C] / [b,C,h,w], and (optionally) zhat_noquant = mu + eps*std in zhat's layout.
+ * eps: fp32 noise in zhat's layout, drawn by the host framework (torch.randn_like keeps RNG parity:
+ * in bchw the reference's randn_like(mu) fills memory in [b,C,h,w] order because mu is a view);
+ * eps == NULL <=> zhat_noquant == NULL.  std = exp(0.5*clamp(logvar, lv_lo, lv_hi)) and log(std)
+ * are evaluated with the libdevice functions torch's own CUDA kernels use. */
+int64_t gq_quantize_latent_workspace_bytes(const gq_codebook_t *cb, int64_t b, int64_t l, int C);
+int gq_quantize_latent(const gq_codebook_t *cb, const float *z, const float *eps, int64_t b,
+                       int64_t l, int C, int layout, float lv_lo, float lv_hi, int64_t *idx,
+                       float *zhat, float *zhat_noquant, void *workspace, int64_t workspace_bytes,
+                       uint32_t *stats, gq_stream_t stream);
+
 /* ---- dequant --------------------------------------------------------------------------
  * idx: int64, [b,l,ncb] (BLC) or [b,ncb,h,w] (BCHW); out: fp32 [b,l,ncb*g] or
  * [b,ncb*g,h,w]; out channel k*ncb + j of a token = codebook[idx[token,j]][k].

@@ -288,3 +288,77 @@ def test_gq2_golden(gq, name):
     assert np.array_equal(reg.dequant(info["indices"]).cpu().numpy(), g["dequant"])
     # STE output: zhat_g - zhat_g.detach() + zhat_v == zhat_v up to one rounding of the cancel
     np.testing.assert_allclose(zhat.detach().cpu().numpy(), g["zhat_quant"], rtol=0, atol=1e-5)
+
+
+# ---- fused front-end: raw latent -> indices / zhat / zhat_noquant in one call ----------
+@pytest.mark.parametrize("fmt,b,spatial,g,N", [
+    ("bchw", 3, (8, 8), 16, 4096), ("blc", 2, 50, 16, 4096), ("bchw", 2, (4, 6), 4, 4096), ("blc", 3, 17, 8, 1000),
+    ("bchw", 4, (32, 32), 16, 65536),
+])
+def test_fused_latent_path_equals_torch_prologue_plus_rows(gq, fmt, b, spatial, g, N):
+    """exp/log/clamp/randn-combine done inside the front-end kernel must be bit-identical to the
+    reference's torch ops on the same device (gaussian.py:62-80,121-123)."""
+    C = 16
+    cb, nlp, h = big_codebook(gq, N, g)
+    gen = torch.Generator().manual_seed(b * 131 + g)
+    if fmt == "bchw":
+        hh, ww = spatial
+        l = hh * ww
+        z = torch.cat([torch.randn(b, C, hh, ww, generator=gen) * 0.8, -1.4 + 0.6 * torch.randn(b, C, hh, ww, generator=gen)], 1)
+        z[0, C:, 0, 0] = 25.0     # exercise the clamp on both sides
+        z[0, C:, 0, 1] = -40.0
+        layout = gq.ops.GQ_LAYOUT_BCHW
+    else:
+        l = spatial
+        z = torch.cat([torch.randn(b, l, C, generator=gen) * 0.8, -1.4 + 0.6 * torch.randn(b, l, C, generator=gen)], 2)
+        z[0, 0, C:] = 25.0
+        z[0, 1, C:] = -40.0
+        layout = gq.ops.GQ_LAYOUT_BLC
+    z = z.cuda()
+    eps_blc = torch.randn(b, l, C, generator=gen).cuda()
+    # the operator takes eps in zhat's layout
+    eps = eps_blc.permute(0, 2, 1).reshape(b, C, *spatial).contiguous() if fmt == "bchw" else eps_blc
+    zq, ind, znq = gq.quantize_latent(h, z, layout, eps, (-30.0, 20.0))
+    # reference torch prologue on the device
+    zz = z.permute(0, 2, 3, 1).reshape(b, l, 2 * C) if fmt == "bchw" else z
+    mu, lv = zz.chunk(2, 2)
+    lv = torch.clamp(lv, -30.0, 20.0)
+    std = torch.exp(0.5 * lv)
+    want_nq = mu + eps_blc * std
+    if fmt == "bchw":
+        want_nq = want_nq.permute(0, 2, 1).reshape(b, C, *spatial)
+    ncb = C // g
+    mu_r = mu.reshape(b, l, g, ncb).permute(0, 1, 3, 2).reshape(-1, g)
+    std_r = std.reshape(b, l, g, ncb).permute(0, 1, 3, 2).reshape(-1, g)
+    idx_rows, zhat_rows = gq.quantize_rows(h, mu_r, std_r, std_r.log())
+    want_ind = idx_rows.reshape(b, l, ncb)
+    want_z = zhat_rows.reshape(b, l, ncb, g).permute(0, 1, 3, 2).reshape(b, l, C)
+    if fmt == "bchw":
+        want_ind = want_ind.permute(0, 2, 1).reshape(b, ncb, *spatial)
+        want_z = want_z.permute(0, 2, 1).reshape(b, C, *spatial)
+    assert torch.equal(znq, want_nq)
+    assert torch.equal(ind, want_ind)
+    assert torch.equal(zq, want_z)
+
+
+def test_module_eval_rng_parity_with_reference_call(gq):
+    """The module must consume the torch RNG exactly like the reference (one randn_like of the
+    [b,l,c] view, gaussian.py:121), so zhat_noquant == mu + randn*std for the same seed."""
+    reg = gq.GaussianQuantRegularizer(format="bchw", n_samples=4096, group=16, backend="cuda").cuda().eval()
+    z = torch.randn(2, 32, 8, 8, device="cuda") * 0.5
+    torch.manual_seed(77)
+    _, info = reg(z)
+    torch.manual_seed(77)
+    from einops import rearrange
+    zz = rearrange(z, "b c h w -> b (h w) c")                 # gaussian.py:69 (a view)
+    mu, lv = zz.chunk(2, 2)
+    std = torch.exp(0.5 * torch.clamp(lv, -30.0, 20.0))
+    want = rearrange(mu + torch.randn_like(mu) * std, "b (h w) c -> b c h w", h=8)   # gaussian.py:121,156
+    assert torch.equal(info["zhat_noquant"], want)
+    # train branch: same noise call (gaussian.py:84)
+    reg.train()
+    torch.manual_seed(78)
+    zhat_t, _ = reg(z)
+    torch.manual_seed(78)
+    want_t = rearrange(mu + torch.randn_like(mu) * std, "b (h w) c -> b c h w", h=8)
+    torch.testing.assert_close(zhat_t, want_t, rtol=1e-6, atol=1e-6)

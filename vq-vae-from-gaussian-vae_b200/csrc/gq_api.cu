@@ -163,6 +163,26 @@ int gq_quantize(const gq_codebook_t *cb, const float *mu, const float *std, cons
                               (cudaStream_t)stream);
 }
 
+int64_t gq_quantize_latent_workspace_bytes(const gq_codebook_t *cb, int64_t b, int64_t l, int C)
+{
+    if (!cb || b < 0 || l < 0 || C <= 0 || C % cb->g) return -1;
+    return latent_workspace_bytes(cb, b * l * (C / cb->g));
+}
+
+int gq_quantize_latent(const gq_codebook_t *cb, const float *z, const float *eps, int64_t b, int64_t l, int C,
+                       int layout, float lv_lo, float lv_hi, int64_t *idx, float *zhat, float *zhat_noquant,
+                       void *workspace, int64_t workspace_bytes, uint32_t *stats, gq_stream_t stream)
+{
+    if (!cb) { set_error("gq_quantize_latent: codebook handle is null"); return GQ_ERR_INVALID; }
+    if (b < 0 || l < 0 || C <= 0) { set_error("gq_quantize_latent: bad sizes"); return GQ_ERR_INVALID; }
+    if (layout != GQ_LAYOUT_BLC && layout != GQ_LAYOUT_BCHW) { set_error("gq_quantize_latent: bad layout %d", layout); return GQ_ERR_INVALID; }
+    if (b * l == 0) return GQ_OK;
+    if (!z || !idx || !zhat) { set_error("gq_quantize_latent: null pointer"); return GQ_ERR_INVALID; }
+    if ((eps == nullptr) != (zhat_noquant == nullptr)) { set_error("gq_quantize_latent: eps and zhat_noquant go together"); return GQ_ERR_INVALID; }
+    return launch_quantize_latent(cb, z, eps, b, l, C, layout, lv_lo, lv_hi, idx, zhat, zhat_noquant, workspace,
+                                  workspace_bytes, stats, (cudaStream_t)stream);
+}
+
 int gq_quantize_exact(const gq_codebook_t *cb, const float *mu, const float *std, const float *log_std,
                       int64_t M, int64_t *idx, float *zhat, gq_stream_t stream)
 {

@@ -26,6 +26,11 @@ int launch_quantize_tc(const gq_codebook *cb, const float *mu, const float *std,
                        int64_t M, int64_t *idx, float *zhat, void *ws, int64_t ws_bytes,
                        uint32_t *stats, cudaStream_t stream);
 
+int64_t latent_workspace_bytes(const gq_codebook *cb, int64_t M);
+int launch_quantize_latent(const gq_codebook *cb, const float *z, const float *eps, int64_t b, int64_t l, int C,
+                           int layout, float lv_lo, float lv_hi, int64_t *idx_out, float *zhat_out, float *zhat_nq,
+                           void *ws, int64_t ws_bytes, uint32_t *stats, cudaStream_t stream);
+
 int debug_tc_scores(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
                     void *ws, int64_t ws_bytes, float *dump, float *wrow_out, cudaStream_t stream);
 void debug_plan(int64_t N, int64_t M, int sms, int64_t *out);

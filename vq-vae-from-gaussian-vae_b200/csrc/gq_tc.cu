@@ -730,7 +730,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
 template <int G, int KPAD>
 static int run_tc(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
                   int64_t *idx, float *zhat, const TcPlan &p, const TcWorkspace &w, uint32_t *stats,
-                  float w_max, cudaStream_t stream)
+                  float w_max, cudaStream_t stream, bool do_prep = true)
 {
     using L = TcSmem<KPAD>;
     static bool attr_set = false;
@@ -743,10 +743,14 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
     cudaError_t e = cudaMemsetAsync(w.counters, 0, 256, stream);
     if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
 
-    rows_prep_kernel<G, KPAD><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
-        mu, std, lstd, cb->meta, w.a_img, w.wrow, w.margin, M, p.M_pad, cb->beta, w_max);
-    int rc = check_launch("rows_prep_kernel");
-    if (rc) return rc;
+    int rc = GQ_OK;
+    if (do_prep) {
+        rows_prep_kernel<G, KPAD><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
+            mu, std, lstd, cb->meta, w.a_img, w.wrow, w.margin, M, p.M_pad, cb->beta, w_max);
+        rc = check_launch("rows_prep_kernel");
+        if (rc) return rc;
+        count_launch(1);
+    }
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (g_prof) {
@@ -772,7 +776,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
     }
     rc = check_launch("rescore_kernel");
     if (rc) return rc;
-    count_launch(3);
+    count_launch(2);
 
     // exact scan over the rows the search could not certify (device-side count, no host sync)
     int fb_blocks = device_sm_count() * 2;
@@ -804,7 +808,198 @@ static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std,
     return GQ_OK;
 }
 
+
+// ---- fused regularizer front-end: raw latent -> rows, operand image, windows, zhat_noquant ----------
+// Replaces the torch prologue of the eval branch (gaussian.py:62-80,121-123: float, rearrange, chunk,
+// clamp, exp, randn*std+mu, the reshape/permute into rows, and std.log()) plus rows_prep_kernel.
+// Thread <-> (token, sub-codebook j), addressing as in gq_kl.cu.  std = exp(0.5*clamp(logvar)) and
+// log(std) use the same libdevice expf/logf torch's CUDA kernels call; zhat_noquant = mu + eps*std is
+// formed with one multiply and one add (no FMA), as torch's two kernels do.
+template <int G, int KPAD>
+__global__ void __launch_bounds__(128)
+frontend_kernel(const float *__restrict__ z, const float *__restrict__ eps, const float *__restrict__ meta,
+                float *__restrict__ mu_r, float *__restrict__ std_r, float *__restrict__ lstd_r,
+                float *__restrict__ zhat_nq, __half *__restrict__ a_img, float *__restrict__ wrow,
+                float *__restrict__ margin, int64_t b, int64_t l, int C, int layout, float lv_lo, float lv_hi,
+                int64_t M, int64_t M_pad, float beta, float w_max)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M_pad) return;
+    const int ncb = C / G;
+    float m[G], s[G], ls[G];
+    int64_t r = i;
+    const bool valid = i < M;
+    if (valid) {
+        // eps / zhat_noquant share zhat's layout: [b,C,h,w] or [b,l,C] (base eb, channel stride es)
+        int64_t zb, zs, lvo, eb, es;
+        if (layout == GQ_LAYOUT_BCHW) {
+            const int64_t t = i % l;
+            const int j = (int)((i / l) % ncb);
+            const int64_t bi = i / (l * ncb);
+            zb = (bi * 2 * C + j) * l + t;
+            zs = (int64_t)ncb * l;
+            lvo = (int64_t)C * l;
+            r = (bi * l + t) * ncb + j;
+            eb = (bi * C + j) * l + t;
+            es = (int64_t)ncb * l;
+        } else {
+            const int j = (int)(i % ncb);
+            const int64_t tok = i / ncb;
+            zb = tok * 2 * C + j;
+            zs = ncb;
+            lvo = C;
+            eb = tok * C + j;
+            es = ncb;
+        }
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            m[k] = __ldg(z + zb + k * zs);
+            const float lv = fminf(fmaxf(__ldg(z + zb + lvo + k * zs), lv_lo), lv_hi);
+            s[k] = expf(__fmul_rn(0.5f, lv));
+            ls[k] = logf(s[k]);
+            if (zhat_nq) zhat_nq[eb + k * es] = __fadd_rn(m[k], __fmul_rn(__ldg(eps + eb + k * es), s[k]));
+        }
+        if constexpr (G % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < G / 4; ++k) {
+                reinterpret_cast<float4 *>(mu_r + r * G)[k] = make_float4(m[4 * k], m[4 * k + 1], m[4 * k + 2], m[4 * k + 3]);
+                reinterpret_cast<float4 *>(std_r + r * G)[k] = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+                reinterpret_cast<float4 *>(lstd_r + r * G)[k] = make_float4(ls[4 * k], ls[4 * k + 1], ls[4 * k + 2], ls[4 * k + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < G; ++k) { mu_r[r * G + k] = m[k]; std_r[r * G + k] = s[k]; lstd_r[r * G + k] = ls[k]; }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < G; ++k) { m[k] = 0.f; s[k] = 1.f; ls[k] = 0.f; }
+    }
+    prep_row<G, KPAD>(m, s, ls, meta, beta, w_max, valid, a_img + r * KPAD, wrow + r, margin + r);
+}
+
+// Row indices -> the module's output tensors (gaussian.py:153-158): indices [b,l,ncb] / [b,ncb,h,w]
+// and zhat [b,l,C] / [b,C,h,w] with channel k*ncb + j = codebook[idx][k].
+template <int G>
+__global__ void __launch_bounds__(256)
+finalize_kernel(const int64_t *__restrict__ idx_rows, const float *__restrict__ cb, int64_t *__restrict__ idx_out,
+                float *__restrict__ zhat_out, int64_t b, int64_t l, int ncb, int layout)
+{
+    const int64_t total = b * l * ncb;
+    const int C = ncb * G;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t bi, t;
+        int j;
+        if (layout == GQ_LAYOUT_BCHW) { t = i % l; j = (int)((i / l) % ncb); bi = i / (l * ncb); }
+        else { j = (int)(i % ncb); t = (i / ncb) % l; bi = i / (l * ncb); }
+        const int64_t r = (bi * l + t) * ncb + j;
+        const int64_t id = idx_rows[r];
+        idx_out[i] = id;
+        float v[G];
+        load_row<G>(cb + id * G, v);
+        if (layout == GQ_LAYOUT_BCHW) {
+            float *o = zhat_out + (bi * C + j) * l + t;
+#pragma unroll
+            for (int k = 0; k < G; ++k) o[(int64_t)k * ncb * l] = v[k];
+        } else {
+            float *o = zhat_out + (bi * l + t) * C + j;
+            if (ncb == 1 && G % 4 == 0) {
+#pragma unroll
+                for (int k = 0; k < G / 4; ++k)
+                    reinterpret_cast<float4 *>(o)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < G; ++k) o[k * ncb] = v[k];
+            }
+        }
+    }
+}
+
+struct LatentWorkspace {
+    float *mu_r, *std_r, *lstd_r;
+    int64_t *idx_rows;
+    void *tc;
+    int64_t tc_bytes;
+    int64_t bytes;
+};
+
+static LatentWorkspace carve_latent(const gq_codebook *cb, int64_t M, void *base)
+{
+    LatentWorkspace w;
+    char *ptr = reinterpret_cast<char *>(base);
+    int64_t off = 0;
+    const int64_t row_bytes = align_up(M * cb->g * 4, 256);
+    w.mu_r = reinterpret_cast<float *>(ptr + off); off += row_bytes;
+    w.std_r = reinterpret_cast<float *>(ptr + off); off += row_bytes;
+    w.lstd_r = reinterpret_cast<float *>(ptr + off); off += row_bytes;
+    w.idx_rows = reinterpret_cast<int64_t *>(ptr + off); off += align_up(M * 8, 256);
+    w.tc = ptr + off;
+    w.tc_bytes = tc_workspace_bytes(cb, M);
+    off += w.tc_bytes;
+    w.bytes = off;
+    return w;
+}
+
+int64_t latent_workspace_bytes(const gq_codebook *cb, int64_t M)
+{
+    return carve_latent(cb, M > 0 ? M : 1, nullptr).bytes;
+}
+
 static float g_w_max = 3.0f;
+
+template <int G, int KPAD>
+static int run_latent(const gq_codebook *cb, const float *z, const float *eps, int64_t b, int64_t l, int C,
+                      int layout, float lv_lo, float lv_hi, int64_t *idx_out, float *zhat_out, float *zhat_nq,
+                      const LatentWorkspace &lw, uint32_t *stats, cudaStream_t stream)
+{
+    const int ncb = C / G;
+    const int64_t M = b * l * ncb;
+    TcPlan p = make_plan(cb, M);
+    TcWorkspace w = carve(cb, p, lw.tc);
+    frontend_kernel<G, KPAD><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
+        z, eps, cb->meta, lw.mu_r, lw.std_r, lw.lstd_r, zhat_nq, w.a_img, w.wrow, w.margin, b, l, C, layout, lv_lo,
+        lv_hi, M, p.M_pad, cb->beta, g_w_max);
+    int rc = check_launch("frontend_kernel");
+    if (rc) return rc;
+    rc = run_tc<G, KPAD>(cb, lw.mu_r, lw.std_r, lw.lstd_r, M, lw.idx_rows, nullptr, p, w, stats, g_w_max, stream,
+                         /*do_prep=*/false);
+    if (rc) return rc;
+    int blocks = (int)imin((M + 255) / 256, (int64_t)device_sm_count() * 8);
+    finalize_kernel<G><<<blocks, 256, 0, stream>>>(lw.idx_rows, cb->cb, idx_out, zhat_out, b, l, ncb, layout);
+    count_launch(2);
+    return check_launch("finalize_kernel");
+}
+
+int launch_quantize_latent(const gq_codebook *cb, const float *z, const float *eps, int64_t b, int64_t l, int C,
+                           int layout, float lv_lo, float lv_hi, int64_t *idx_out, float *zhat_out, float *zhat_nq,
+                           void *ws, int64_t ws_bytes, uint32_t *stats, cudaStream_t stream)
+{
+    if (C % cb->g) { set_error("channels %d not divisible by group %d", C, cb->g); return GQ_ERR_INVALID; }
+    const int64_t M = b * l * (C / cb->g);
+    if (M == 0) return GQ_OK;
+    if (M >= ((int64_t)1 << 31)) { set_error("M too large"); return GQ_ERR_INVALID; }
+    if (device_cc_major() != 10) {
+        set_error("gq_quantize_latent needs an sm_100 device (tcgen05/TMEM); found cc major %d", device_cc_major());
+        return GQ_ERR_UNSUPPORTED;
+    }
+    LatentWorkspace lw = carve_latent(cb, M, ws);
+    if (ws == nullptr || ws_bytes < lw.bytes) {
+        set_error("workspace too small: need %lld bytes, got %lld", (long long)lw.bytes, (long long)ws_bytes);
+        return GQ_ERR_WORKSPACE;
+    }
+    if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) { set_error("workspace must be 256-byte aligned"); return GQ_ERR_INVALID; }
+#define GQ_LAT(GG, KK) return run_latent<GG, KK>(cb, z, eps, b, l, C, layout, lv_lo, lv_hi, idx_out, zhat_out, zhat_nq, lw, stats, stream)
+    switch (cb->g) {
+    case 1: GQ_LAT(1, 16);
+    case 2: GQ_LAT(2, 16);
+    case 4: GQ_LAT(4, 16);
+    case 8: GQ_LAT(8, 16);
+    case 16: GQ_LAT(16, 32);
+    case 32: GQ_LAT(32, 64);
+    default: set_error("group %d unsupported", cb->g); return GQ_ERR_INVALID;
+    }
+#undef GQ_LAT
+}
+
 void set_tc_window_max(float w) { g_w_max = w; }
 
 int launch_quantize_tc(const gq_codebook *cb, const float *mu, const float *std, const float *lstd,

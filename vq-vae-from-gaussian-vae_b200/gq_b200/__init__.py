@@ -10,10 +10,11 @@ from . import _lib
 _lib.lib()  # fail loudly at import time if the CUDA library is absent or stale
 
 from . import ops  # noqa: E402
-from .ops import Codebook, dequant, kl_penalty, launch_count, quantize_rows, scores_legacy_  # noqa: E402
+from .ops import (Codebook, dequant, kl_penalty, launch_count, quantize_latent, quantize_rows,  # noqa: E402
+                  scores_legacy_)
 from .regularizer import GaussianQuantRegularizer, GaussianQuantRegularizer2, prior_samples  # noqa: E402
 
 __all__ = [
-    "ops", "Codebook", "quantize_rows", "dequant", "kl_penalty", "scores_legacy_", "launch_count",
+    "ops", "Codebook", "quantize_rows", "quantize_latent", "dequant", "kl_penalty", "scores_legacy_", "launch_count",
     "GaussianQuantRegularizer", "GaussianQuantRegularizer2", "prior_samples",
 ]

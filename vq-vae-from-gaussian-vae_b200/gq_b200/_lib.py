@@ -33,6 +33,9 @@ PROTOTYPES = {
     "gq_quantize_workspace_bytes": (c_int64, [c_void_p, c_int64]),
     "gq_quantize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                             c_void_p, c_int64, c_void_p, c_void_p]),
+    "gq_quantize_latent_workspace_bytes": (c_int64, [c_void_p, c_int64, c_int64, c_int]),
+    "gq_quantize_latent": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_float,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "gq_quantize_exact": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                   c_void_p, c_void_p]),
     "gq_dequant": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import GQ_LAYOUT_BCHW, GQ_LAYOUT_BLC, check
 
 __all__ = [
-    "Codebook", "scores_legacy_", "quantize_rows", "dequant", "kl_penalty", "launch_count",
+    "Codebook", "scores_legacy_", "quantize_rows", "quantize_latent", "dequant", "kl_penalty", "launch_count",
     "GQ_LAYOUT_BLC", "GQ_LAYOUT_BCHW",
 ]
 
@@ -98,6 +98,16 @@ class Codebook:
 
     def workspace(self, M: int) -> torch.Tensor:
         need = int(_lib.lib().gq_quantize_workspace_bytes(self.handle, M))
+        return self._grow(need)
+
+    def latent_workspace(self, b: int, l: int, C: int) -> torch.Tensor:
+        need = int(_lib.lib().gq_quantize_latent_workspace_bytes(self.handle, b, l, C))
+        if need < 0:
+            raise RuntimeError(f"latent with {C} channels does not fit group {self.g}")
+        return self._grow(need)
+
+    def _grow(self, need: int) -> torch.Tensor:
+        # one cached scratch buffer per handle; calls on one stream are ordered, so reuse is safe
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
@@ -147,6 +157,52 @@ def quantize_rows(cb: Codebook, mu: torch.Tensor, std: torch.Tensor,
                                          _ptr(zhat), _ptr(ws), ws.numel(), _ptr(stats), _stream()),
                   "gq_quantize")
     return idx, zhat
+
+
+def quantize_latent(cb: Codebook, z: torch.Tensor, layout: int, eps: Optional[torch.Tensor] = None,
+                    logvar_range=(-30.0, 20.0), stats: Optional[torch.Tensor] = None):
+    """The whole eval branch from the raw latent (gaussian.py:62-80,121-159) in one C call.
+
+    z fp32 [b,l,2C] (BLC) or [b,2C,h,w] (BCHW); eps fp32 noise shaped like zhat, or None.
+    Returns (zhat, indices, zhat_noquant), all in z's layout (zhat_noquant None without eps)."""
+    _require_cuda_f32("z", z)
+    if z.device != cb.device:
+        raise RuntimeError("latent and codebook live on different devices")
+    z = z.contiguous()
+    if layout == GQ_LAYOUT_BCHW:
+        if z.dim() != 4:
+            raise RuntimeError("bchw latent must be [b, 2C, h, w]")
+        b, c2, h, w = z.shape
+        l = h * w
+    else:
+        if z.dim() != 3:
+            raise RuntimeError("blc latent must be [b, l, 2C]")
+        b, l, c2 = z.shape
+    C = c2 // 2
+    if c2 != 2 * C or C % cb.g:
+        raise RuntimeError(f"latent channels {c2} do not split into (mu | logvar) groups of {cb.g}")
+    ncb = C // cb.g
+    if layout == GQ_LAYOUT_BCHW:
+        zhat = torch.empty(b, C, h, w, dtype=torch.float32, device=z.device)
+        idx = torch.empty(b, ncb, h, w, dtype=torch.int64, device=z.device)
+    else:
+        zhat = torch.empty(b, l, C, dtype=torch.float32, device=z.device)
+        idx = torch.empty(b, l, ncb, dtype=torch.int64, device=z.device)
+    znq = None
+    if eps is not None:
+        _require_cuda_f32("eps", eps)
+        if eps.shape != zhat.shape:
+            raise RuntimeError(f"eps must be shaped like zhat {tuple(zhat.shape)}, got {tuple(eps.shape)}")
+        eps = eps.contiguous()
+        znq = torch.empty_like(zhat)
+    if b * l == 0:
+        return zhat, idx, znq
+    ws = cb.latent_workspace(b, l, C)
+    with torch.cuda.device(z.device):
+        check(_lib.lib().gq_quantize_latent(cb.handle, _ptr(z), _ptr(eps), b, l, C, layout, float(logvar_range[0]),
+                                            float(logvar_range[1]), _ptr(idx), _ptr(zhat), _ptr(znq), _ptr(ws),
+                                            ws.numel(), _ptr(stats), _stream()), "gq_quantize_latent")
+    return zhat, idx, znq
 
 
 def dequant(cb: Codebook, indices: torch.Tensor, layout: int, check_range: bool = False) -> torch.Tensor:

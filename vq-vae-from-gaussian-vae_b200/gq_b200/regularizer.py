@@ -34,6 +34,20 @@ __all__ = ["prior_samples", "GaussianQuantRegularizer", "GaussianQuantRegularize
 from gq_b200_host import normal_log_prob as _normal_log_prob, prior_samples  # noqa: E402,F401
 
 
+def _reference_noise(b: int, l: int, c: int, bchw: bool, hw, device) -> torch.Tensor:
+    """torch.randn_like(mu) exactly as the reference issues it (gaussian.py:84,121), returned in
+    zhat's layout.  mu is a chunk VIEW of the blc latent; in bchw format that latent is itself a
+    rearrange view of z, so mu has strides (2c*l, 1, l) and randn_like fills memory in [b,c,l]
+    order -- i.e. the noise comes out as a contiguous [b,c,h,w] tensor.  Reproducing the same
+    call on an empty tensor with those strides keeps the RNG stream bit-identical."""
+    if bchw:
+        proto = torch.empty_strided((b, l, c), (2 * c * l, 1, l), dtype=torch.float32, device=device)
+        eps = torch.randn_like(proto)               # strides (c*l, 1, l)
+        return eps.transpose(1, 2).reshape(b, c, *hw)   # free view: contiguous [b,c,h,w]
+    proto = torch.empty_strided((b, l, c), (l * 2 * c, 2 * c, 1), dtype=torch.float32, device=device)
+    return torch.randn_like(proto)
+
+
 class _GQBase(nn.Module):
     """State shared by both regularizer variants: codebook buffers + prepared device handle."""
 
@@ -111,12 +125,7 @@ class GaussianQuantRegularizer(_GQBase):
         else:
             b, l, c2 = z.shape
             c = c2 // 2
-        # the reference draws torch.randn_like(mu) with mu a [b,l,c] chunk view of the blc
-        # latent (gaussian.py:76,84); reproduce the same call so the RNG stream is identical
-        proto = torch.empty_strided((b, l, c), (l * 2 * c, 2 * c, 1), dtype=torch.float32, device=z.device)
-        eps = torch.randn_like(proto)
-        if layout == GQ_LAYOUT_BCHW:
-            eps = eps.permute(0, 2, 1).reshape(b, c, h, w)
+        eps = _reference_noise(b, l, c, layout == GQ_LAYOUT_BCHW, (h, w) if layout == GQ_LAYOUT_BCHW else None, z.device)
         zhat, kl_loss, stats = ops.kl_penalty(
             z, eps, self.group, layout, self.logvar_range, float(self.log_n_samples), self.tolerance,
             self.lam, self.lam_min, self.lam_max)
@@ -131,33 +140,17 @@ class GaussianQuantRegularizer(_GQBase):
     def _forward_eval(self, z: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
         if self.backend not in ("cuda", "torch"):
             raise ValueError
-        g = self.group
-        if self.format == "bchw":
-            b, c, h, w = z.shape
-            c = c // 2
-            l = h * w
-            zhat = z.permute(0, 2, 3, 1).reshape(b, l, 2 * c)
+        layout = GQ_LAYOUT_BCHW if self.format == "bchw" else GQ_LAYOUT_BLC
+        if layout == GQ_LAYOUT_BCHW:
+            b, c2, h, w = z.shape
+            l, c = h * w, c2 // 2
         else:
-            b, l, c = z.shape
-            c = c // 2
-            zhat = z
-        ncb = c // g
-        mu, logvar = zhat.chunk(2, 2)
-        logvar = torch.clamp(logvar, self.logvar_range[0], self.logvar_range[1])
-        std = torch.exp(0.5 * logvar)
-        zhat_noquant = mu + torch.randn_like(mu) * std
-        mu_r = mu.reshape(b, l, g, ncb).permute(0, 1, 3, 2).reshape(-1, g)
-        std_r = std.reshape(b, l, g, ncb).permute(0, 1, 3, 2).reshape(-1, g)
-        cb = self._codebook()
-        idx, _ = ops.quantize_rows(cb, mu_r, std_r, std_r.log(), stats=self.last_stats)
-        indices = idx.reshape(b, l, ncb)
-        if self.format == "bchw":
-            indices = indices.permute(0, 2, 1).reshape(b, ncb, h, w).contiguous()
-            zhat_noquant = zhat_noquant.permute(0, 2, 1).reshape(b, c, h, w)
-            zq = ops.dequant(cb, indices, GQ_LAYOUT_BCHW)
-        else:
-            zq = ops.dequant(cb, indices, GQ_LAYOUT_BLC)
-        return zq, {"indices": indices, "zhat_noquant": zhat_noquant}
+            b, l, c2 = z.shape
+            c = c2 // 2
+        eps = _reference_noise(b, l, c, layout == GQ_LAYOUT_BCHW, (h, w) if layout == GQ_LAYOUT_BCHW else None, z.device)
+        zq, indices, znq = ops.quantize_latent(self._codebook(), z, layout, eps, self.logvar_range,
+                                               stats=self.last_stats)
+        return zq, {"indices": indices, "zhat_noquant": znq}
 
     def forward(self, z):
         z = z.float()
