@@ -15,6 +15,10 @@ int launch_quantize_exact(const gq_codebook *cb, const float *mu, const float *s
                           const uint32_t *row_count, int64_t *idx, float *zhat, int max_blocks,
                           cudaStream_t stream);
 
+int launch_exact_sliced(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
+                        const uint32_t *row_list, const uint32_t *row_count, unsigned long long *keys,
+                        uint32_t *done, int64_t *idx, float *zhat, cudaStream_t stream);
+
 int launch_codebook_prep(gq_codebook *cb, const float *nlp_in, cudaStream_t stream);
 
 int launch_dequant(const gq_codebook *cb, const int64_t *idx, float *out, int64_t b, int64_t l,

@@ -217,6 +217,145 @@ int launch_quantize_exact(const gq_codebook *cb, const float *mu, const float *s
 }
 
 // ------------------------------------------------------------------------------------------
+// Sliced exact scan: the fallback of the tensor-core search.  Work item = (group of kExactRows
+// listed rows, slice of the codebook); a block scores its slice in the reference op order and merges
+// its per-row winners into packed 64-bit keys with atomicMax:
+//   key = monotone_u32(score) << 32 | (0xffffffff - index)      (higher score wins, ties -> lower index)
+// The block that completes a row group (arrival counter) turns the keys into idx / zhat.  A handful of
+// fallback rows thus spreads over the whole GPU instead of serialising 65536 codewords in one block.
+// keys[r] must be 0 when the row is listed (the listing kernels do that); done[] is zeroed per call.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_key(float s, int n)
+{
+    uint32_t u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+}
+
+template <int G>
+__global__ void __launch_bounds__(kExactThreads)
+exact_sliced_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
+                    const float *__restrict__ cb, const float *__restrict__ nlpb, int64_t N,
+                    const uint32_t *__restrict__ row_list, const uint32_t *__restrict__ row_count, int slices,
+                    unsigned long long *__restrict__ keys, uint32_t *__restrict__ done,
+                    int64_t *__restrict__ idx_out, float *__restrict__ zhat_out)
+{
+    __shared__ float s_mu[kExactRows][G], s_den[kExactRows][G], s_ls[kExactRows][G];
+    __shared__ int64_t s_row[kExactRows];
+    __shared__ unsigned long long s_key[kExactRows][kExactThreads / 32];
+    __shared__ bool s_last;
+    const int64_t total = (int64_t)(*row_count);
+    const int64_t groups = (total + kExactRows - 1) / kExactRows;
+    const int64_t per = ((N + slices - 1) / slices + kExactThreads - 1) / kExactThreads * kExactThreads;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int64_t item = blockIdx.x; item < groups * slices; item += gridDim.x) {
+        const int64_t grp = item / slices;
+        const int sl = (int)(item % slices);
+        const int64_t base = grp * kExactRows;
+        const int rows = (int)imin((int64_t)kExactRows, total - base);
+        __syncthreads();
+        if (tid < kExactRows) s_row[tid] = tid < rows ? (int64_t)row_list[base + tid] : -1;
+        __syncthreads();
+        for (int i = tid; i < kExactRows * G; i += kExactThreads) {
+            const int rr = i / G, k = i % G;
+            const int64_t r = s_row[rr];
+            float m = 0.f, sd = 1.f, l = 0.f;
+            if (r >= 0) {
+                m = mu[r * G + k];
+                sd = std[r * G + k];
+                l = lstd ? lstd[r * G + k] : logf(sd);
+            }
+            s_mu[rr][k] = m;
+            s_den[rr][k] = __fmul_rn(2.0f, __fmul_rn(sd, sd));
+            s_ls[rr][k] = l;
+        }
+        __syncthreads();
+        unsigned long long best[kExactRows];
+#pragma unroll
+        for (int r = 0; r < kExactRows; ++r) best[r] = 0ull;
+        const int64_t lo = (int64_t)sl * per, hi = imin(N, lo + per);
+        for (int64_t n = lo + tid; n < hi; n += kExactThreads) {
+            float x[G], nb[G];
+            load_row<G>(cb + n * G, x);
+            load_row<G>(nlpb + n * G, nb);
+#pragma unroll
+            for (int r = 0; r < kExactRows; ++r) {
+                float t[G];
+#pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    float d = __fsub_rn(x[k], s_mu[r][k]);
+                    float d2 = __fmul_rn(d, d);
+                    float q = __fdiv_rn(-d2, s_den[r][k]);
+                    float a = __fsub_rn(q, s_ls[r][k]);
+                    float b = __fsub_rn(a, GQ_C0F);
+                    t[k] = __fsub_rn(b, nb[k]);
+                }
+                const float sc = sum_torch_inner<G>(t);
+                if (sc == sc) {   // NaN never wins here; torch.argmax would pick it, documented divergence
+                    const unsigned long long key = pack_key(sc, (int)n);
+                    if (key > best[r]) best[r] = key;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kExactRows; ++r) {
+            unsigned long long b = best[r];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, b, off);
+                if (o > b) b = o;
+            }
+            if (lane == 0) s_key[r][warp] = b;
+        }
+        __syncthreads();
+        if (tid < rows) {
+            unsigned long long b = s_key[tid][0];
+            for (int w = 1; w < kExactThreads / 32; ++w) if (s_key[tid][w] > b) b = s_key[tid][w];
+            if (b) atomicMax(&keys[s_row[tid]], b);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(&done[grp], 1u) == (uint32_t)(slices - 1));
+        __syncthreads();
+        if (s_last && tid < rows) {
+            __threadfence();
+            const int64_t r = s_row[tid];
+            const unsigned long long key = atomicMax(&keys[r], 0ull);   // coherent read
+            const int64_t bi = key ? (int64_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull)) : 0;  // all NaN: torch gives 0
+            idx_out[r] = bi;
+            if (zhat_out) {
+#pragma unroll
+                for (int k = 0; k < G; ++k) zhat_out[r * G + k] = cb[bi * G + k];
+            }
+        }
+    }
+}
+
+int launch_exact_sliced(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
+                        const uint32_t *row_list, const uint32_t *row_count, unsigned long long *keys,
+                        uint32_t *done, int64_t *idx, float *zhat, cudaStream_t stream)
+{
+    (void)M;
+    const int slices = (int)imax(1, imin(64, cb->N / 1024));
+    const int blocks = device_sm_count() * 4;
+#define GQ_XS(GG) exact_sliced_kernel<GG><<<blocks, kExactThreads, 0, stream>>>(mu, std, lstd, cb->cb, cb->nlpb, cb->N, \
+        row_list, row_count, slices, keys, done, idx, zhat)
+    switch (cb->g) {
+    case 1: GQ_XS(1); break;
+    case 2: GQ_XS(2); break;
+    case 4: GQ_XS(4); break;
+    case 8: GQ_XS(8); break;
+    case 16: GQ_XS(16); break;
+    case 32: GQ_XS(32); break;
+    default: set_error("group %d unsupported", cb->g); return GQ_ERR_INVALID;
+    }
+#undef GQ_XS
+    count_launch();
+    return check_launch("exact_sliced_kernel");
+}
+
+// ------------------------------------------------------------------------------------------
 // Codebook preparation (once per codebook, off the hot path).
 //   nlpb[n,k] = nlp[n,k]*beta (one fp32 rounding, gaussian.py:143-144); nlp itself, when not
 //   supplied, is Normal(0,1).log_prob(x) in torch's op order (gaussian.py:51-52).

@@ -83,8 +83,17 @@ constexpr int kCap = 32;             // chunk records per (row, segment)
 constexpr int kChunk = 32;           // columns per recorded chunk
 constexpr int kMinStepsPerCta = 8;
 
-struct __align__(8) SegHdr { float runmax; uint32_t cnt; };
 struct __align__(8) Cand { float score; uint32_t idx; };  // idx = chunk id (codeword / 32)
+
+// Per (row, segment) summary written by the epilogue thread when its piece ends: the segment's running
+// maximum and its records already filtered against that maximum (score >= runmax - w), so that the
+// rescoring kernel fetches everything it needs about a segment with one 64-byte read.
+// cnt: number of surviving records (<= kSurv), or kSegOverflow if the record list or the survivor
+// slots overflowed (the row then goes to the exact scan).
+constexpr int kSurv = 7;
+constexpr uint32_t kSegOverflow = 0xffffffffu;
+struct __align__(16) SegHdr { float runmax; uint32_t cnt; Cand surv[kSurv]; };
+static_assert(sizeof(SegHdr) == 64, "segment summary must be 64 bytes");
 
 struct TcPlan {
     int64_t M, M_pad, N;
@@ -124,8 +133,12 @@ struct TcWorkspace {
     float *margin;      // [M_pad] prefilter margin (unscaled score units)
     SegHdr *seg;        // [M_pad, nseg]
     Cand *cand;         // [M_pad, nseg, kCap]
-    uint32_t *fb_rows;  // [M] fallback row list
-    uint32_t *counters; // [0] fallback count
+    uint32_t *fb_rows;  // [M] fallback row list (exact scan)
+    uint32_t *st_rows;  // [M] rows whose prefilter left several contenders (settle_kernel); bit 31: use the full record list
+    uint32_t *rec_cnt;  // [M_pad, nseg] records written per (row, segment) (may exceed kCap: list overflow)
+    unsigned long long *fb_keys;  // [M] packed (score, ~index) argmax keys of the sliced exact scan
+    uint32_t *counters; // [0] fallback count, [1] settle count, [64..] per-row-group arrival counters of the scan
+    int64_t counter_bytes;
     int64_t bytes;
 };
 
@@ -148,8 +161,15 @@ static TcWorkspace carve(const gq_codebook *cb, const TcPlan &p, void *base)
     off = align_up(off + p.M_pad * p.nseg * (int64_t)kCap * (int64_t)sizeof(Cand), 256);
     w.fb_rows = reinterpret_cast<uint32_t *>(ptr + off);
     off = align_up(off + p.M * 4, 256);
+    w.st_rows = reinterpret_cast<uint32_t *>(ptr + off);
+    off = align_up(off + p.M * 4, 256);
+    w.rec_cnt = reinterpret_cast<uint32_t *>(ptr + off);
+    off = align_up(off + p.M_pad * p.nseg * 4, 256);
+    w.fb_keys = reinterpret_cast<unsigned long long *>(ptr + off);
+    off = align_up(off + p.M * 8, 256);
     w.counters = reinterpret_cast<uint32_t *>(ptr + off);
-    off = align_up(off + 256, 256);
+    w.counter_bytes = align_up(256 + (p.M / 8 + 2) * 4, 256);
+    off += w.counter_bytes;
     w.bytes = off;
     return w;
 }
@@ -331,8 +351,8 @@ template <int KPAD, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
 quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ b_img,
                    const float *__restrict__ wrow, SegHdr *__restrict__ seg_hdr, Cand *__restrict__ cand,
-                   int64_t N, int tiles, int64_t total_steps, int steps_per_cta, int nseg,
-                   float *__restrict__ dump)
+                   uint32_t *__restrict__ rec_cnt, int64_t N, int tiles, int64_t total_steps, int steps_per_cta,
+                   int nseg, float *__restrict__ dump)
 {
     using L = TcSmem<KPAD>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -512,7 +532,26 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                     }
                 }
             }
-            seg_hdr[row * nseg + p.seg] = SegHdr{runmax, cnt};
+            // piece done: filter this thread's own records against its final maximum and publish the
+            // survivors (typically one or two) in the 64-byte segment summary
+            {
+                SegHdr *hp = &seg_hdr[row * nseg + p.seg];
+                uint32_t ns = 0;
+                bool ovf = cnt > (uint32_t)kCap;
+                const float keep = runmax - w;
+                const uint32_t nrec = cnt < (uint32_t)kCap ? cnt : (uint32_t)kCap;
+                for (uint32_t i = 0; i < nrec; ++i) {
+                    const Cand c = list[i];
+                    if (c.score >= keep) {
+                        if (ns < (uint32_t)kSurv) hp->surv[ns] = c;
+                        else ovf = true;
+                        ++ns;
+                    }
+                }
+                hp->runmax = runmax;
+                hp->cnt = ovf ? kSegOverflow : ns;
+                rec_cnt[row * nseg + p.seg] = cnt;
+            }
         }
     }
 
@@ -541,181 +580,251 @@ __device__ __forceinline__ float prefilter_score(const float (&x)[G], const floa
     return a2;
 }
 
-// Rare path of the rescoring kernel (a few percent of rows): several codewords lie within the
-// prefilter margin of the best one; settle them in the reference's exact fp32 op order.  Kept out of
-// line so that its register needs do not lower the occupancy of the common path.
+constexpr int kMaxChunks = 64;   // surviving chunks one row may carry into the rescoring (else: exact scan)
+
+// Rows whose fp32 prefilter left more than one contender (a few percent): one warp per listed row
+// re-reads the segment summaries and scores every codeword of the surviving chunks (lane = codeword)
+// in the reference's exact fp32 op order; first-max tie-break.  Runs after rescore_kernel, before the
+// exact-scan fallback (to which it can still defer a row with non-finite scores).
 template <int G>
-__device__ __noinline__ int settle_exact(const float *__restrict__ par /* [4][G] smem: mu, den, lstd, 1/den */,
-                                         const float *__restrict__ cb, const float *__restrict__ nlpb,
-                                         const SegHdr *__restrict__ seg_row, const Cand *__restrict__ cand_row,
-                                         int npieces, int64_t N, float thr, float lim, float hb, int lane)
+__global__ void __launch_bounds__(128)
+settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
+              const float *__restrict__ cb, const float *__restrict__ nlpb, const float *__restrict__ wrow,
+              const SegHdr *__restrict__ seg_hdr, const Cand *__restrict__ cand, const uint32_t *__restrict__ rec_cnt,
+              const uint32_t *__restrict__ rows, const uint32_t *__restrict__ nrows, int64_t N, int tiles,
+              int steps_per_cta, int nseg, int64_t *__restrict__ idx_out, float *__restrict__ zhat_out,
+              uint32_t *__restrict__ fb_rows, uint32_t *__restrict__ fb_count, unsigned long long *__restrict__ fb_keys)
 {
-    float m[G], den[G], ls[G], ri[G];
+    const int lane = threadIdx.x & 31;
+    const uint32_t total = *nrows;
+    for (uint32_t it = blockIdx.x * 4 + (threadIdx.x >> 5); it < total; it += gridDim.x * 4) {
+        const uint32_t entry = rows[it];
+        const bool full = (entry & 0x80000000u) != 0u;   // a segment kept more than kSurv survivors: walk its full list
+        const int64_t r = entry & 0x7fffffffu;
+        const uint32_t s0 = (uint32_t)(r / kUnitRows) * (uint32_t)tiles;
+        const int npieces = (int)((s0 + (uint32_t)tiles - 1u) / (uint32_t)steps_per_cta) - (int)(s0 / (uint32_t)steps_per_cta) + 1;
+        float gmax = -CUDART_INF_F;
+        for (int s = 0; s < npieces; ++s) gmax = fmaxf(gmax, seg_hdr[r * nseg + s].runmax);
+        const float thr = gmax - wrow[r];
+        float m[G], den[G], ls[G];
+        load_row<G>(mu + r * G, m);
+        {
+            float sd[G];
+            load_row<G>(std + r * G, sd);
 #pragma unroll
-    for (int k = 0; k < G; ++k) { m[k] = par[k]; den[k] = par[G + k]; ls[k] = par[2 * G + k]; ri[k] = par[3 * G + k]; }
-    float best = -CUDART_INF_F;
-    int best_idx = 0x7fffffff;
-    for (int s = 0; s < npieces; ++s) {
-        const SegHdr h = seg_row[s];
-        const Cand c = cand_row[(int64_t)s * kCap + lane];
-        unsigned surv = __ballot_sync(0xffffffffu, (uint32_t)lane < h.cnt && c.score >= thr);
-        while (surv) {
-            const int i = __ffs(surv) - 1;
-            surv &= surv - 1;
-            const uint32_t chunk = __shfl_sync(0xffffffffu, c.idx, i);
-            const int64_t n = (int64_t)chunk * kChunk + lane;
-            if (n < N) {
-                float x[G];
-                load_row<G>(cb + n * G, x);
-                const float a2 = prefilter_score<G>(x, m, ri, hb);
-                if (a2 >= lim) {
-                    float nb[G];
+            for (int k = 0; k < G; ++k) {
+                den[k] = __fmul_rn(2.0f, __fmul_rn(sd[k], sd[k]));
+                ls[k] = lstd ? __ldg(lstd + r * G + k) : logf(sd[k]);
+            }
+        }
+        float best = -CUDART_INF_F;
+        int best_idx = 0x7fffffff;
+        for (int s = 0; s < npieces; ++s) {
+            const SegHdr *h = &seg_hdr[r * nseg + s];
+            const Cand *list = full ? cand + (r * nseg + s) * (int64_t)kCap : h->surv;
+            const uint32_t cnt = full ? rec_cnt[r * nseg + s] : h->cnt;   // <= kCap resp. <= kSurv by construction
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const Cand c = list[i];
+                if (!(c.score >= thr)) continue;
+                const int64_t n = (int64_t)c.idx * kChunk + lane;
+                if (n < N) {
+                    float x[G], nb[G];
+                    load_row<G>(cb + n * G, x);
                     load_row<G>(nlpb + n * G, nb);
                     const float sc = score_exact<G>(x, nb, m, den, ls);
                     if (sc > best || (sc == best && (int)n < best_idx)) { best = sc; best_idx = (int)n; }
                 }
             }
         }
-    }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
-        if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
+            if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+        }
+        if (best_idx == 0x7fffffff || !(best > -CUDART_INF_F)) {
+            if (lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
+        } else {
+            if (lane == 0) idx_out[r] = (int64_t)best_idx;
+            if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
+        }
     }
-    if (!(best > -CUDART_INF_F)) best_idx = 0x7fffffff;
-    return best_idx;
 }
 
+struct RowIn { float w, margin, pm, ps, pl; uint4 q; int npieces; };
+
+template <int G>
+__device__ __forceinline__ RowIn fetch_row(int64_t r, int lane, const float *__restrict__ wrow,
+                                           const float *__restrict__ margin_row, const SegHdr *__restrict__ seg_hdr,
+                                           const float *__restrict__ mu, const float *__restrict__ std,
+                                           const float *__restrict__ lstd, int tiles, int steps_per_cta, int nseg)
+{
+    RowIn in;
+    const int seg_l = lane >> 2, quarter = lane & 3;
+    in.w = __ldg(wrow + r);
+    in.margin = __ldg(margin_row + r);
+    // total_steps < 2^31 (checked on the host), so the step arithmetic fits 32 bits (a 64-bit
+    // divide would be an out-of-line call)
+    const uint32_t s0 = (uint32_t)(r / kUnitRows) * (uint32_t)tiles;
+    in.npieces = (int)((s0 + (uint32_t)tiles - 1u) / (uint32_t)steps_per_cta) - (int)(s0 / (uint32_t)steps_per_cta) + 1;
+    in.q = make_uint4(0u, 0u, 0u, 0u);
+    if (seg_l < in.npieces) in.q = __ldg(reinterpret_cast<const uint4 *>(seg_hdr + r * nseg + seg_l) + quarter);
+    in.pm = in.ps = in.pl = 0.f;
+    if (lane < G) {
+        in.pm = __ldg(mu + r * G + lane);
+        in.ps = __ldg(std + r * G + lane);
+        if (lstd) in.pl = __ldg(lstd + r * G + lane);
+    }
+    return in;
+}
+
+// One warp per row.  All a row needs arrives in ONE round of independent loads (window, margin, the
+// 64-byte summaries of up to eight segments -- lane i takes 16-byte quarter i%4 of segment i/4 -- and
+// mu/std/log std on lanes < g), issued one row ahead so that the round trip overlaps the previous
+// row's math.  The surviving chunks' codewords (lane = codeword) are the second and last round.
 template <int G>
 __global__ void __launch_bounds__(kRescoreWarps * 32, (G <= 16) ? 3 : 1)
 rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
                const float *__restrict__ cb, const float *__restrict__ nlpb, const float *__restrict__ wrow,
-               const float *__restrict__ margin_row, const SegHdr *__restrict__ seg_hdr,
-               const Cand *__restrict__ cand, int64_t M, int64_t N, int tiles, int steps_per_cta, int nseg,
-               float beta, int64_t *__restrict__ idx_out, float *__restrict__ zhat_out,
-               uint32_t *__restrict__ fb_rows, uint32_t *__restrict__ fb_count, uint32_t *__restrict__ stats)
+               const float *__restrict__ margin_row, const SegHdr *__restrict__ seg_hdr, int64_t M, int64_t N,
+               int tiles, int steps_per_cta, int nseg, float beta, int64_t *__restrict__ idx_out,
+               float *__restrict__ zhat_out, uint32_t *__restrict__ fb_rows, uint32_t *__restrict__ fb_count,
+               uint32_t *__restrict__ settle_rows, uint32_t *__restrict__ settle_count,
+               const uint32_t *__restrict__ rec_cnt, unsigned long long *__restrict__ fb_keys,
+               uint32_t *__restrict__ stats)
 {
-    __shared__ float s_par[kRescoreWarps][4][G];   // mu, den, log std, 1/den of the warp's row
+    __shared__ float s_par[kRescoreWarps][4][G];          // mu, den, log std, 1/den of the warp's row
+    __shared__ uint32_t s_chunks[kRescoreWarps][kMaxChunks];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t warp_global = (int64_t)blockIdx.x * kRescoreWarps + wib;
     const int64_t nwarps = (int64_t)gridDim.x * kRescoreWarps;
     const float hb = 0.5f * beta;
+    const int seg_l = lane >> 2, quarter = lane & 3;
     uint32_t st_rows = 0, st_pre = 0, st_exact = 0, st_fb = 0, st_ovf = 0;
-    constexpr int kFast = 2;   // segments whose headers + records are fetched in one round of loads
 
+    RowIn cur{}, nxt{};
+    if (warp_global < M) cur = fetch_row<G>(warp_global, lane, wrow, margin_row, seg_hdr, mu, std, lstd, tiles, steps_per_cta, nseg);
     for (int64_t r = warp_global; r < M; r += nwarps) {
-        const float w = wrow[r];
-        bool fallback = !(w >= 0.f);
-        bool overflow = false;
+        const bool has_next = r + nwarps < M;
+        if (has_next)   // in flight while this row is processed
+            nxt = fetch_row<G>(r + nwarps, lane, wrow, margin_row, seg_hdr, mu, std, lstd, tiles, steps_per_cta, nseg);
+
+        bool fallback = !(cur.w >= 0.f);
+        bool overflow = false, settle = false, settle_full = false;
         int best_idx = 0x7fffffff;
         if (!fallback) {
-            const int unit = (int)(r / kUnitRows);
-            const int64_t s0 = (int64_t)unit * tiles;
-            const int first = (int)(s0 / steps_per_cta);
-            const int last = (int)((s0 + tiles - 1) / steps_per_cta);
-            const int npieces = last - first + 1;
-            // one round of independent loads: headers and (speculatively, all kCap slots) records of the
-            // first kFast segments, lane i taking record i; slots >= cnt are ignored below
-            SegHdr hd[kFast];
-            Cand rec[kFast];
-#pragma unroll
-            for (int s = 0; s < kFast; ++s) {
-                hd[s] = SegHdr{-CUDART_INF_F, 0u};
-                rec[s] = Cand{-CUDART_INF_F, 0u};
-                if (s < npieces) {
-                    hd[s] = seg_hdr[r * nseg + s];
-                    rec[s] = cand[(r * nseg + s) * (int64_t)kCap + lane];
+            const int npieces = cur.npieces;
+            // ---- pass A: global maximum / overflow over all segments (groups of eight) ----
+            float gmax = -CUDART_INF_F;
+            for (int base = 0; base < npieces; base += 8) {
+                uint4 q = cur.q;
+                if (base > 0) {
+                    q = make_uint4(0u, 0u, 0u, 0u);
+                    if (base + seg_l < npieces) q = __ldg(reinterpret_cast<const uint4 *>(seg_hdr + r * nseg + base + seg_l) + quarter);
+                }
+                const bool head = (quarter == 0) && (base + seg_l < npieces);
+                if (head) {
+                    gmax = fmaxf(gmax, __uint_as_float(q.x));
+                    if (q.y == kSegOverflow) overflow = true;
                 }
             }
-            const float margin = margin_row[r];
-            __syncwarp();
-            if (lane < G) {
-                const float sd = __ldg(std + r * G + lane);
-                const float dn = __fmul_rn(2.0f, __fmul_rn(sd, sd));
-                s_par[wib][0][lane] = __ldg(mu + r * G + lane);
-                s_par[wib][1][lane] = dn;
-                s_par[wib][2][lane] = lstd ? __ldg(lstd + r * G + lane) : logf(sd);
-                s_par[wib][3][lane] = 1.0f / dn;
-            }
-            float gmax = -CUDART_INF_F;
 #pragma unroll
-            for (int s = 0; s < kFast; ++s) {
-                gmax = fmaxf(gmax, hd[s].runmax);
-                if (hd[s].cnt > (uint32_t)kCap) overflow = true;
-            }
-            for (int s = kFast; s < npieces; ++s) {
-                SegHdr h = seg_hdr[r * nseg + s];
-                gmax = fmaxf(gmax, h.runmax);
-                if (h.cnt > (uint32_t)kCap) overflow = true;
-            }
-            __syncwarp();
-            if (overflow || !(gmax > -CUDART_INF_F)) fallback = true;
+            for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+            overflow = __any_sync(0xffffffffu, overflow);
+            if (overflow && gmax > -CUDART_INF_F) {
+                // some segment kept more than kSurv survivors (or overflowed its record list): if every
+                // record list is intact the settle kernel walks them, otherwise the row takes the exact scan
+                bool lost = false;
+                for (int s = lane; s < npieces; s += 32) lost |= rec_cnt[r * nseg + s] > (uint32_t)kCap;
+                if (__any_sync(0xffffffffu, lost)) fallback = true;
+                else { settle = true; settle_full = true; }
+            } else if (!(gmax > -CUDART_INF_F)) fallback = true;
             else {
-                const float thr = gmax - w;
-                float m[G], ri[G];
+                const float thr = gmax - cur.w;
+                // ---- pass B: surviving chunk ids -> shared memory ----
+                int nchunks = 0;
+                for (int base = 0; base < npieces; base += 8) {
+                    uint4 q = cur.q;
+                    if (base > 0) {
+                        q = make_uint4(0u, 0u, 0u, 0u);
+                        if (base + seg_l < npieces) q = __ldg(reinterpret_cast<const uint4 *>(seg_hdr + r * nseg + base + seg_l) + quarter);
+                    }
+                    const uint32_t cnt = __shfl_sync(0xffffffffu, q.y, lane & ~3);   // from the segment's head lane
+                    const bool live = base + seg_l < npieces;
+                    // quarter 0 holds survivor 0 in (z,w); quarter k>0 holds survivors 2k-1 in (x,y) and 2k in (z,w)
+                    const uint32_t slot_a = quarter == 0 ? 0u : (uint32_t)(2 * quarter - 1);
+                    const float sc_a = __uint_as_float(quarter == 0 ? q.z : q.x);
+                    const uint32_t id_a = quarter == 0 ? q.w : q.y;
+                    const bool ok_a = live && slot_a < cnt && sc_a >= thr;
+                    const bool ok_b = live && quarter > 0 && (uint32_t)(2 * quarter) < cnt && __uint_as_float(q.z) >= thr;
+                    const unsigned ma = __ballot_sync(0xffffffffu, ok_a);
+                    const unsigned mb = __ballot_sync(0xffffffffu, ok_b);
+                    const unsigned lt = (1u << lane) - 1u;
+                    const int pa = nchunks + __popc(ma & lt);
+                    const int pb = nchunks + __popc(ma) + __popc(mb & lt);
+                    if (ok_a && pa < kMaxChunks) s_chunks[wib][pa] = id_a;
+                    if (ok_b && pb < kMaxChunks) s_chunks[wib][pb] = q.w;
+                    nchunks += __popc(ma) + __popc(mb);
+                }
+                if (lane < G) {
+                    const float dn = __fmul_rn(2.0f, __fmul_rn(cur.ps, cur.ps));
+                    s_par[wib][0][lane] = cur.pm;
+                    s_par[wib][1][lane] = dn;
+                    s_par[wib][2][lane] = lstd ? cur.pl : logf(cur.ps);
+                    s_par[wib][3][lane] = 1.0f / dn;
+                }
+                __syncwarp();
+                if (nchunks == 0 || nchunks > kMaxChunks) fallback = true;
+                else {
+                    float m[G], ri[G];
 #pragma unroll
-                for (int k = 0; k < G; ++k) { m[k] = s_par[wib][0][k]; ri[k] = s_par[wib][3][k]; }
-
-                // pass 1: fp32 FMA prefilter over the surviving chunks, per-lane best and runner-up
-                float a_best = -CUDART_INF_F, a_second = -CUDART_INF_F;
-                int n_best = 0x7fffffff;
-                auto scan = [&](uint32_t cnt, const Cand &c) {
-                    unsigned surv = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && c.score >= thr);
-                    while (surv) {
-                        const int i = __ffs(surv) - 1;
-                        surv &= surv - 1;
-                        const uint32_t chunk = __shfl_sync(0xffffffffu, c.idx, i);
-                        const int64_t n = (int64_t)chunk * kChunk + lane;
-                        st_pre += 1;
-                        if (n < N) {
-                            float x[G];
-                            load_row<G>(cb + n * G, x);
-                            const float a2 = prefilter_score<G>(x, m, ri, hb);
-                            if (a2 > a_best) { a_second = a_best; a_best = a2; n_best = (int)n; }
+                    for (int k = 0; k < G; ++k) { m[k] = s_par[wib][0][k]; ri[k] = s_par[wib][3][k]; }
+                    // ---- fp32 FMA prefilter over the surviving chunks ----
+                    float a_best = -CUDART_INF_F, a_second = -CUDART_INF_F;
+                    int n_best = 0x7fffffff;
+                    st_pre += (uint32_t)nchunks;
+                    for (int c = 0; c < nchunks; ++c) {
+                        const int64_t n0 = (int64_t)s_chunks[wib][c] * kChunk + lane;
+                        if (n0 < N) {
+                            float x0[G];
+                            load_row<G>(cb + n0 * G, x0);
+                            const float a2 = prefilter_score<G>(x0, m, ri, hb);
+                            if (a2 > a_best) { a_second = a_best; a_best = a2; n_best = (int)n0; }
                             else if (a2 > a_second) a_second = a2;
                         }
                     }
-                };
+                    float g2 = a_best;
 #pragma unroll
-                for (int s = 0; s < kFast; ++s) scan(hd[s].cnt, rec[s]);
-                for (int s = kFast; s < npieces; ++s) {
-                    const SegHdr h = seg_hdr[r * nseg + s];
-                    const Cand c = cand[(r * nseg + s) * (int64_t)kCap + lane];
-                    scan(h.cnt, c);
+                    for (int off = 16; off > 0; off >>= 1) g2 = fmaxf(g2, __shfl_xor_sync(0xffffffffu, g2, off));
+                    const float lim = g2 - cur.margin;
+                    const unsigned firsts = __ballot_sync(0xffffffffu, a_best >= lim);
+                    const unsigned seconds = __ballot_sync(0xffffffffu, a_second >= lim);
+                    if (!(g2 > -CUDART_INF_F) || !(cur.margin >= 0.f) || firsts == 0u) {
+                        fallback = true;   // NaN / -inf rows: let the scan decide
+                    } else if (__popc(firsts) == 1 && seconds == 0u) {
+                        best_idx = __shfl_sync(0xffffffffu, n_best, __ffs(firsts) - 1);
+                    } else {
+                        // several codewords within the prefilter margin: settle_kernel decides in the exact op order
+                        st_exact += 1;
+                        settle = true;
+                    }
                 }
-                float g2 = a_best;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) g2 = fmaxf(g2, __shfl_xor_sync(0xffffffffu, g2, off));
-                const float lim = g2 - margin;
-                const unsigned firsts = __ballot_sync(0xffffffffu, a_best >= lim);
-                const unsigned seconds = __ballot_sync(0xffffffffu, a_second >= lim);
-                if (!(g2 > -CUDART_INF_F) || !(margin >= 0.f) || firsts == 0u) {
-                    fallback = true;   // NaN / -inf rows: let the scan decide
-                } else if (__popc(firsts) == 1 && seconds == 0u) {
-                    best_idx = __shfl_sync(0xffffffffu, n_best, __ffs(firsts) - 1);
-                } else {
-                    // several codewords within the prefilter margin: settle them in the exact op order
-                    st_exact += 1;
-                    best_idx = settle_exact<G>(&s_par[wib][0][0], cb, nlpb, seg_hdr + r * nseg,
-                                               cand + r * nseg * (int64_t)kCap, npieces, N, thr, lim, hb, lane);
-                    if (best_idx == 0x7fffffff) fallback = true;
-                }
+                __syncwarp();
             }
         }
         if (fallback) {
-            if (lane == 0) {
-                uint32_t slot = atomicAdd(fb_count, 1u);
-                fb_rows[slot] = (uint32_t)r;
-            }
+            if (lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
             st_fb += 1;
+        } else if (settle) {
+            if (lane == 0) settle_rows[atomicAdd(settle_count, 1u)] = (uint32_t)r | (settle_full ? 0x80000000u : 0u);
         } else {
             if (lane == 0) idx_out[r] = (int64_t)best_idx;
             if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
         }
         st_rows += 1;
         st_ovf += overflow ? 1u : 0u;
+        if (has_next) cur = nxt;
     }
     if (stats && lane == 0) {
         atomicAdd(&stats[0], st_rows);
@@ -740,7 +849,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
         attr_set = true;
     }
-    cudaError_t e = cudaMemsetAsync(w.counters, 0, 256, stream);
+    cudaError_t e = cudaMemsetAsync(w.counters, 0, (size_t)w.counter_bytes, stream);
     if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
 
     int rc = GQ_OK;
@@ -759,7 +868,8 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
         cudaEventRecord(ev0, stream);
     }
     quantize_tc_kernel<KPAD, false><<<p.ctas, kThreads, L::kBytes, stream>>>(
-        w.a_img, cb->bimg, w.wrow, w.seg, w.cand, cb->N, p.tiles, p.total_steps, p.steps_per_cta, p.nseg, nullptr);
+        w.a_img, cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N, p.tiles, p.total_steps, p.steps_per_cta, p.nseg,
+        nullptr);
     if (g_prof) {
         cudaEventRecord(ev1, stream);
         g_prof_events.emplace_back(ev0, ev1);
@@ -771,16 +881,22 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
         int64_t need = (M + kRescoreWarps - 1) / kRescoreWarps;
         int blocks = (int)imin(need, (int64_t)device_sm_count() * 8);
         rescore_kernel<G><<<blocks, kRescoreWarps * 32, 0, stream>>>(
-            mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.margin, w.seg, w.cand, M, cb->N, p.tiles, p.steps_per_cta,
-            p.nseg, cb->beta, idx, zhat, w.fb_rows, w.counters, stats);
+            mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.margin, w.seg, M, cb->N, p.tiles, p.steps_per_cta, p.nseg,
+            cb->beta, idx, zhat, w.fb_rows, w.counters, w.st_rows, w.counters + 1, w.rec_cnt, w.fb_keys, stats);
+        rc = check_launch("rescore_kernel");
+        if (rc) return rc;
+        int sblocks = (int)imin((M + 3) / 4, (int64_t)device_sm_count() * 8);
+        settle_kernel<G><<<sblocks, 128, 0, stream>>>(mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.seg, w.cand, w.rec_cnt,
+                                                      w.st_rows, w.counters + 1, cb->N, p.tiles, p.steps_per_cta, p.nseg,
+                                                      idx, zhat, w.fb_rows, w.counters, w.fb_keys);
     }
-    rc = check_launch("rescore_kernel");
+    rc = check_launch("settle_kernel");
     if (rc) return rc;
-    count_launch(2);
+    count_launch(3);
 
-    // exact scan over the rows the search could not certify (device-side count, no host sync)
-    int fb_blocks = device_sm_count() * 2;
-    return launch_quantize_exact(cb, mu, std, lstd, M, w.fb_rows, w.counters, idx, zhat, fb_blocks, stream);
+    // exact scan over the rows the search could not certify (device-side count, no host sync),
+    // sliced over the codebook so that a handful of rows still spreads over the whole GPU
+    return launch_exact_sliced(cb, mu, std, lstd, M, w.fb_rows, w.counters, w.fb_keys, w.counters + 64, idx, zhat, stream);
 }
 
 // Debug/diagnostic path (tests only): runs row prep + the search with the DUMP epilogue and
@@ -799,7 +915,8 @@ static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std,
     int rc = check_launch("rows_prep_kernel");
     if (rc) return rc;
     quantize_tc_kernel<KPAD, true><<<p.ctas, kThreads, L::kBytes, stream>>>(
-        w.a_img, cb->bimg, w.wrow, w.seg, w.cand, cb->N, p.tiles, p.total_steps, p.steps_per_cta, p.nseg, dump);
+        w.a_img, cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N, p.tiles, p.total_steps, p.steps_per_cta, p.nseg,
+        dump);
     rc = check_launch("quantize_tc_kernel<dump>");
     if (rc) return rc;
     e = cudaMemcpyAsync(wrow_out, w.wrow, sizeof(float) * p.M_pad, cudaMemcpyDeviceToDevice, stream);
@@ -976,7 +1093,10 @@ int launch_quantize_latent(const gq_codebook *cb, const float *z, const float *e
     if (C % cb->g) { set_error("channels %d not divisible by group %d", C, cb->g); return GQ_ERR_INVALID; }
     const int64_t M = b * l * (C / cb->g);
     if (M == 0) return GQ_OK;
-    if (M >= ((int64_t)1 << 31)) { set_error("M too large"); return GQ_ERR_INVALID; }
+    if (M >= ((int64_t)1 << 31) || (M / kUnitRows + 1) * (cb->n_pad / kTileN) >= ((int64_t)1 << 31)) {
+        set_error("problem too large: rows x codebook tiles must stay below 2^31");
+        return GQ_ERR_INVALID;
+    }
     if (device_cc_major() != 10) {
         set_error("gq_quantize_latent needs an sm_100 device (tcgen05/TMEM); found cc major %d", device_cc_major());
         return GQ_ERR_UNSUPPORTED;
@@ -1007,7 +1127,10 @@ int launch_quantize_tc(const gq_codebook *cb, const float *mu, const float *std,
                        cudaStream_t stream)
 {
     if (M == 0) return GQ_OK;
-    if (M >= ((int64_t)1 << 31)) { set_error("M too large"); return GQ_ERR_INVALID; }
+    if (M >= ((int64_t)1 << 31) || (M / kUnitRows + 1) * (cb->n_pad / kTileN) >= ((int64_t)1 << 31)) {
+        set_error("problem too large: rows x codebook tiles must stay below 2^31");
+        return GQ_ERR_INVALID;
+    }
     if (device_cc_major() != 10) {
         set_error("gq_quantize needs an sm_100 device (tcgen05/TMEM); found cc major %d", device_cc_major());
         return GQ_ERR_UNSUPPORTED;
