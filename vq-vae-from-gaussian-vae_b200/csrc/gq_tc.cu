@@ -200,8 +200,16 @@ template <int G, int KPAD>
 __device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G], const float (&ls)[G],
                                          const float *__restrict__ meta, float beta, float w_max, bool valid,
                                          __half *__restrict__ a_row, float *__restrict__ w_out,
-                                         float *__restrict__ margin_out)
+                                         float *__restrict__ margin_out, SegHdr *__restrict__ seg_row,
+                                         uint32_t *__restrict__ rec_row, int nseg)
 {
+    // segments no CTA will touch must read as empty: (runmax, cnt) = (-inf, 0), no records
+    if (valid) {
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+            *reinterpret_cast<uint2 *>(&seg_row[sgi]) = make_uint2(0xff800000u, 0u);
+            rec_row[sgi] = 0u;
+        }
+    }
     float A[2 * G];
     bool bad = !valid;
     float amax = 0.f, bnorm2 = 0.f, R = 0.f, p_naive = 0.f, maxA = 0.f, sumA = 0.f, eA = 0.f;
@@ -262,7 +270,8 @@ template <int G, int KPAD>
 __global__ void __launch_bounds__(128)
 rows_prep_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
                  const float *__restrict__ meta, __half *__restrict__ a_img, float *__restrict__ wrow,
-                 float *__restrict__ margin, int64_t M, int64_t M_pad, float beta, float w_max)
+                 float *__restrict__ margin, SegHdr *__restrict__ seg_hdr, uint32_t *__restrict__ rec_cnt, int nseg,
+                 int64_t M, int64_t M_pad, float beta, float w_max)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= M_pad) return;
@@ -280,7 +289,8 @@ rows_prep_kernel(const float *__restrict__ mu, const float *__restrict__ std, co
 #pragma unroll
         for (int k = 0; k < G; ++k) { m[k] = 0.f; s[k] = 1.f; ls[k] = 0.f; }
     }
-    prep_row<G, KPAD>(m, s, ls, meta, beta, w_max, valid, a_img + r * KPAD, wrow + r, margin + r);
+    prep_row<G, KPAD>(m, s, ls, meta, beta, w_max, valid, a_img + r * KPAD, wrow + r, margin + r,
+                      seg_hdr + r * nseg, rec_cnt + r * nseg, nseg);
 }
 
 // ---- 2. the tensor-core search ------------------------------------------------------------------
@@ -651,24 +661,20 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
     }
 }
 
-struct RowIn { float w, margin, pm, ps, pl; uint4 q; int npieces; };
+struct RowIn { float w, margin, pm, ps, pl; uint4 q; };
 
 template <int G>
 __device__ __forceinline__ RowIn fetch_row(int64_t r, int lane, const float *__restrict__ wrow,
                                            const float *__restrict__ margin_row, const SegHdr *__restrict__ seg_hdr,
                                            const float *__restrict__ mu, const float *__restrict__ std,
-                                           const float *__restrict__ lstd, int tiles, int steps_per_cta, int nseg)
+                                           const float *__restrict__ lstd, int nseg)
 {
     RowIn in;
     const int seg_l = lane >> 2, quarter = lane & 3;
     in.w = __ldg(wrow + r);
     in.margin = __ldg(margin_row + r);
-    // total_steps < 2^31 (checked on the host), so the step arithmetic fits 32 bits (a 64-bit
-    // divide would be an out-of-line call)
-    const uint32_t s0 = (uint32_t)(r / kUnitRows) * (uint32_t)tiles;
-    in.npieces = (int)((s0 + (uint32_t)tiles - 1u) / (uint32_t)steps_per_cta) - (int)(s0 / (uint32_t)steps_per_cta) + 1;
-    in.q = make_uint4(0u, 0u, 0u, 0u);
-    if (seg_l < in.npieces) in.q = __ldg(reinterpret_cast<const uint4 *>(seg_hdr + r * nseg + seg_l) + quarter);
+    in.q = make_uint4(0xff800000u, 0u, 0xff800000u, 0u);
+    if (seg_l < nseg) in.q = __ldg(reinterpret_cast<const uint4 *>(seg_hdr + r * nseg + seg_l) + quarter);
     in.pm = in.ps = in.pl = 0.f;
     if (lane < G) {
         in.pm = __ldg(mu + r * G + lane);
@@ -679,110 +685,106 @@ __device__ __forceinline__ RowIn fetch_row(int64_t r, int lane, const float *__r
 }
 
 // One warp per row.  All a row needs arrives in ONE round of independent loads (window, margin, the
-// 64-byte summaries of up to eight segments -- lane i takes 16-byte quarter i%4 of segment i/4 -- and
-// mu/std/log std on lanes < g), issued one row ahead so that the round trip overlaps the previous
-// row's math.  The surviving chunks' codewords (lane = codeword) are the second and last round.
+// 64-byte summaries of its <= 8 segments -- lane i takes 16-byte quarter i%4 of segment i/4; untouched
+// segments read as empty -- and mu/std/log std on lanes < g), issued one row ahead so that the round
+// trip overlaps the previous row's math.  The surviving chunks' codewords (lane = codeword) are the
+// second and last round.  Plans with more than 8 segments per row (tiny M, huge N) send every row to
+// settle_kernel instead.
 template <int G>
 __global__ void __launch_bounds__(kRescoreWarps * 32, (G <= 16) ? 3 : 1)
 rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
-               const float *__restrict__ cb, const float *__restrict__ nlpb, const float *__restrict__ wrow,
-               const float *__restrict__ margin_row, const SegHdr *__restrict__ seg_hdr, int64_t M, int64_t N,
-               int tiles, int steps_per_cta, int nseg, float beta, int64_t *__restrict__ idx_out,
-               float *__restrict__ zhat_out, uint32_t *__restrict__ fb_rows, uint32_t *__restrict__ fb_count,
-               uint32_t *__restrict__ settle_rows, uint32_t *__restrict__ settle_count,
-               const uint32_t *__restrict__ rec_cnt, unsigned long long *__restrict__ fb_keys,
-               uint32_t *__restrict__ stats)
+               const float *__restrict__ cb, const float *__restrict__ wrow, const float *__restrict__ margin_row,
+               const SegHdr *__restrict__ seg_hdr, int64_t M, int64_t N, int nseg, float beta,
+               int64_t *__restrict__ idx_out, float *__restrict__ zhat_out, uint32_t *__restrict__ fb_rows,
+               uint32_t *__restrict__ fb_count, uint32_t *__restrict__ settle_rows,
+               uint32_t *__restrict__ settle_count, const uint32_t *__restrict__ rec_cnt,
+               unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats)
 {
-    __shared__ float s_par[kRescoreWarps][4][G];          // mu, den, log std, 1/den of the warp's row
+    __shared__ __align__(16) float s_par[kRescoreWarps][2][G < 4 ? 4 : G];   // mu, 1/den of the warp's row
     __shared__ uint32_t s_chunks[kRescoreWarps][kMaxChunks];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t warp_global = (int64_t)blockIdx.x * kRescoreWarps + wib;
     const int64_t nwarps = (int64_t)gridDim.x * kRescoreWarps;
     const float hb = 0.5f * beta;
-    const int seg_l = lane >> 2, quarter = lane & 3;
+    const int quarter = lane & 3;
+    const bool head = quarter == 0;
+    const unsigned lt = (1u << lane) - 1u;
     uint32_t st_rows = 0, st_pre = 0, st_exact = 0, st_fb = 0, st_ovf = 0;
 
-    RowIn cur{}, nxt{};
-    if (warp_global < M) cur = fetch_row<G>(warp_global, lane, wrow, margin_row, seg_hdr, mu, std, lstd, tiles, steps_per_cta, nseg);
-    for (int64_t r = warp_global; r < M; r += nwarps) {
-        const bool has_next = r + nwarps < M;
-        if (has_next)   // in flight while this row is processed
-            nxt = fetch_row<G>(r + nwarps, lane, wrow, margin_row, seg_hdr, mu, std, lstd, tiles, steps_per_cta, nseg);
-
-        bool fallback = !(cur.w >= 0.f);
-        bool overflow = false, settle = false, settle_full = false;
-        int best_idx = 0x7fffffff;
-        if (!fallback) {
-            const int npieces = cur.npieces;
-            // ---- pass A: global maximum / overflow over all segments (groups of eight) ----
-            float gmax = -CUDART_INF_F;
-            for (int base = 0; base < npieces; base += 8) {
-                uint4 q = cur.q;
-                if (base > 0) {
-                    q = make_uint4(0u, 0u, 0u, 0u);
-                    if (base + seg_l < npieces) q = __ldg(reinterpret_cast<const uint4 *>(seg_hdr + r * nseg + base + seg_l) + quarter);
-                }
-                const bool head = (quarter == 0) && (base + seg_l < npieces);
-                if (head) {
-                    gmax = fmaxf(gmax, __uint_as_float(q.x));
-                    if (q.y == kSegOverflow) overflow = true;
-                }
+    if (nseg > 8) {
+        // every row walks its full record lists in settle_kernel (unless a list overflowed)
+        for (int64_t r = warp_global; r < M; r += nwarps) {
+            bool lost = !(wrow[r] >= 0.f);
+            for (int sgi = lane; sgi < nseg; sgi += 32) lost |= rec_cnt[r * nseg + sgi] > (uint32_t)kCap;
+            lost = __any_sync(0xffffffffu, lost);
+            if (lane == 0) {
+                if (lost) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
+                else settle_rows[atomicAdd(settle_count, 1u)] = (uint32_t)r | 0x80000000u;
             }
+            st_rows += 1;
+            st_fb += lost ? 1u : 0u;
+        }
+    } else {
+        RowIn cur{}, nxt{};
+        if (warp_global < M) cur = fetch_row<G>(warp_global, lane, wrow, margin_row, seg_hdr, mu, std, lstd, nseg);
+        for (int64_t r = warp_global; r < M; r += nwarps) {
+            const bool has_next = r + nwarps < M;
+            if (has_next)   // in flight while this row is processed
+                nxt = fetch_row<G>(r + nwarps, lane, wrow, margin_row, seg_hdr, mu, std, lstd, nseg);
+
+            int verdict = 0;   // 0 = decided here, 1 = settle (summaries), 2 = settle (full lists), 3 = exact scan
+            int best_idx = 0;
+            const uint4 q = cur.q;
+            float gmax = head ? __uint_as_float(q.x) : -CUDART_INF_F;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
-            overflow = __any_sync(0xffffffffu, overflow);
-            if (overflow && gmax > -CUDART_INF_F) {
-                // some segment kept more than kSurv survivors (or overflowed its record list): if every
-                // record list is intact the settle kernel walks them, otherwise the row takes the exact scan
+            const bool overflow = __any_sync(0xffffffffu, head && q.y == kSegOverflow);
+            if (!(cur.w >= 0.f) || !(gmax > -CUDART_INF_F)) verdict = 3;
+            else if (overflow) {
                 bool lost = false;
-                for (int s = lane; s < npieces; s += 32) lost |= rec_cnt[r * nseg + s] > (uint32_t)kCap;
-                if (__any_sync(0xffffffffu, lost)) fallback = true;
-                else { settle = true; settle_full = true; }
-            } else if (!(gmax > -CUDART_INF_F)) fallback = true;
-            else {
+                if (lane < nseg) lost = rec_cnt[r * nseg + lane] > (uint32_t)kCap;
+                verdict = __any_sync(0xffffffffu, lost) ? 3 : 2;
+            } else {
                 const float thr = gmax - cur.w;
-                // ---- pass B: surviving chunk ids -> shared memory ----
-                int nchunks = 0;
-                for (int base = 0; base < npieces; base += 8) {
-                    uint4 q = cur.q;
-                    if (base > 0) {
-                        q = make_uint4(0u, 0u, 0u, 0u);
-                        if (base + seg_l < npieces) q = __ldg(reinterpret_cast<const uint4 *>(seg_hdr + r * nseg + base + seg_l) + quarter);
-                    }
-                    const uint32_t cnt = __shfl_sync(0xffffffffu, q.y, lane & ~3);   // from the segment's head lane
-                    const bool live = base + seg_l < npieces;
-                    // quarter 0 holds survivor 0 in (z,w); quarter k>0 holds survivors 2k-1 in (x,y) and 2k in (z,w)
-                    const uint32_t slot_a = quarter == 0 ? 0u : (uint32_t)(2 * quarter - 1);
-                    const float sc_a = __uint_as_float(quarter == 0 ? q.z : q.x);
-                    const uint32_t id_a = quarter == 0 ? q.w : q.y;
-                    const bool ok_a = live && slot_a < cnt && sc_a >= thr;
-                    const bool ok_b = live && quarter > 0 && (uint32_t)(2 * quarter) < cnt && __uint_as_float(q.z) >= thr;
-                    const unsigned ma = __ballot_sync(0xffffffffu, ok_a);
-                    const unsigned mb = __ballot_sync(0xffffffffu, ok_b);
-                    const unsigned lt = (1u << lane) - 1u;
-                    const int pa = nchunks + __popc(ma & lt);
-                    const int pb = nchunks + __popc(ma) + __popc(mb & lt);
-                    if (ok_a && pa < kMaxChunks) s_chunks[wib][pa] = id_a;
-                    if (ok_b && pb < kMaxChunks) s_chunks[wib][pb] = q.w;
-                    nchunks += __popc(ma) + __popc(mb);
-                }
+                // surviving chunk ids -> shared memory
+                // quarter 0 holds survivor 0 in (z,w); quarter k>0 holds survivors 2k-1 in (x,y) and 2k in (z,w)
+                const uint32_t cnt = __shfl_sync(0xffffffffu, q.y, lane & ~3);
+                const uint32_t slot_a = head ? 0u : (uint32_t)(2 * quarter - 1);
+                const float sc_a = __uint_as_float(head ? q.z : q.x);
+                const uint32_t id_a = head ? q.w : q.y;
+                const bool ok_a = slot_a < cnt && sc_a >= thr;
+                const bool ok_b = !head && (uint32_t)(2 * quarter) < cnt && __uint_as_float(q.z) >= thr;
+                const unsigned ma = __ballot_sync(0xffffffffu, ok_a);
+                const unsigned mb = __ballot_sync(0xffffffffu, ok_b);
+                const int na = __popc(ma);
+                const int nchunks = na + __popc(mb);
+                if (ok_a) s_chunks[wib][__popc(ma & lt)] = id_a;               // <= 8*7 = 56 < kMaxChunks
+                if (ok_b) s_chunks[wib][na + __popc(mb & lt)] = q.w;
                 if (lane < G) {
                     const float dn = __fmul_rn(2.0f, __fmul_rn(cur.ps, cur.ps));
                     s_par[wib][0][lane] = cur.pm;
-                    s_par[wib][1][lane] = dn;
-                    s_par[wib][2][lane] = lstd ? cur.pl : logf(cur.ps);
-                    s_par[wib][3][lane] = 1.0f / dn;
+                    s_par[wib][1][lane] = 1.0f / dn;
                 }
                 __syncwarp();
-                if (nchunks == 0 || nchunks > kMaxChunks) fallback = true;
+                if (nchunks == 0) verdict = 3;
                 else {
                     float m[G], ri[G];
+                    if constexpr (G % 4 == 0) {
 #pragma unroll
-                    for (int k = 0; k < G; ++k) { m[k] = s_par[wib][0][k]; ri[k] = s_par[wib][3][k]; }
-                    // ---- fp32 FMA prefilter over the surviving chunks ----
+                        for (int k = 0; k < G / 4; ++k) {
+                            const float4 a = reinterpret_cast<const float4 *>(&s_par[wib][0][0])[k];
+                            const float4 c = reinterpret_cast<const float4 *>(&s_par[wib][1][0])[k];
+                            m[4 * k] = a.x; m[4 * k + 1] = a.y; m[4 * k + 2] = a.z; m[4 * k + 3] = a.w;
+                            ri[4 * k] = c.x; ri[4 * k + 1] = c.y; ri[4 * k + 2] = c.z; ri[4 * k + 3] = c.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < G; ++k) { m[k] = s_par[wib][0][k]; ri[k] = s_par[wib][1][k]; }
+                    }
+                    // fp32 FMA prefilter over the surviving chunks: per-lane best and runner-up
                     float a_best = -CUDART_INF_F, a_second = -CUDART_INF_F;
-                    int n_best = 0x7fffffff;
+                    int n_best = 0;
                     st_pre += (uint32_t)nchunks;
                     for (int c = 0; c < nchunks; ++c) {
                         const int64_t n0 = (int64_t)s_chunks[wib][c] * kChunk + lane;
@@ -800,31 +802,25 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                     const float lim = g2 - cur.margin;
                     const unsigned firsts = __ballot_sync(0xffffffffu, a_best >= lim);
                     const unsigned seconds = __ballot_sync(0xffffffffu, a_second >= lim);
-                    if (!(g2 > -CUDART_INF_F) || !(cur.margin >= 0.f) || firsts == 0u) {
-                        fallback = true;   // NaN / -inf rows: let the scan decide
-                    } else if (__popc(firsts) == 1 && seconds == 0u) {
-                        best_idx = __shfl_sync(0xffffffffu, n_best, __ffs(firsts) - 1);
-                    } else {
-                        // several codewords within the prefilter margin: settle_kernel decides in the exact op order
-                        st_exact += 1;
-                        settle = true;
-                    }
+                    if (!(g2 > -CUDART_INF_F) || !(cur.margin >= 0.f) || firsts == 0u) verdict = 3;   // NaN / -inf rows
+                    else if (__popc(firsts) == 1 && seconds == 0u) best_idx = __shfl_sync(0xffffffffu, n_best, __ffs(firsts) - 1);
+                    else verdict = 1;   // several codewords within the prefilter margin: exact op order decides
                 }
                 __syncwarp();
             }
+            if (verdict == 0) {
+                if (lane == 0) idx_out[r] = (int64_t)best_idx;
+                if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
+            } else if (lane == 0) {
+                if (verdict == 3) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
+                else settle_rows[atomicAdd(settle_count, 1u)] = (uint32_t)r | (verdict == 2 ? 0x80000000u : 0u);
+            }
+            st_rows += 1;
+            st_exact += verdict == 1 ? 1u : 0u;
+            st_fb += verdict == 3 ? 1u : 0u;
+            st_ovf += overflow ? 1u : 0u;
+            if (has_next) cur = nxt;
         }
-        if (fallback) {
-            if (lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
-            st_fb += 1;
-        } else if (settle) {
-            if (lane == 0) settle_rows[atomicAdd(settle_count, 1u)] = (uint32_t)r | (settle_full ? 0x80000000u : 0u);
-        } else {
-            if (lane == 0) idx_out[r] = (int64_t)best_idx;
-            if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
-        }
-        st_rows += 1;
-        st_ovf += overflow ? 1u : 0u;
-        if (has_next) cur = nxt;
     }
     if (stats && lane == 0) {
         atomicAdd(&stats[0], st_rows);
@@ -855,7 +851,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
     int rc = GQ_OK;
     if (do_prep) {
         rows_prep_kernel<G, KPAD><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
-            mu, std, lstd, cb->meta, w.a_img, w.wrow, w.margin, M, p.M_pad, cb->beta, w_max);
+            mu, std, lstd, cb->meta, w.a_img, w.wrow, w.margin, w.seg, w.rec_cnt, p.nseg, M, p.M_pad, cb->beta, w_max);
         rc = check_launch("rows_prep_kernel");
         if (rc) return rc;
         count_launch(1);
@@ -881,8 +877,8 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
         int64_t need = (M + kRescoreWarps - 1) / kRescoreWarps;
         int blocks = (int)imin(need, (int64_t)device_sm_count() * 8);
         rescore_kernel<G><<<blocks, kRescoreWarps * 32, 0, stream>>>(
-            mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.margin, w.seg, M, cb->N, p.tiles, p.steps_per_cta, p.nseg,
-            cb->beta, idx, zhat, w.fb_rows, w.counters, w.st_rows, w.counters + 1, w.rec_cnt, w.fb_keys, stats);
+            mu, std, lstd, cb->cb, w.wrow, w.margin, w.seg, M, cb->N, p.nseg, cb->beta, idx, zhat, w.fb_rows,
+            w.counters, w.st_rows, w.counters + 1, w.rec_cnt, w.fb_keys, stats);
         rc = check_launch("rescore_kernel");
         if (rc) return rc;
         int sblocks = (int)imin((M + 3) / 4, (int64_t)device_sm_count() * 8);
@@ -911,7 +907,7 @@ static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std,
                                          L::kBytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
     rows_prep_kernel<G, KPAD><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
-        mu, std, lstd, cb->meta, w.a_img, w.wrow, w.margin, M, p.M_pad, cb->beta, w_max);
+        mu, std, lstd, cb->meta, w.a_img, w.wrow, w.margin, w.seg, w.rec_cnt, p.nseg, M, p.M_pad, cb->beta, w_max);
     int rc = check_launch("rows_prep_kernel");
     if (rc) return rc;
     quantize_tc_kernel<KPAD, true><<<p.ctas, kThreads, L::kBytes, stream>>>(
@@ -937,8 +933,9 @@ __global__ void __launch_bounds__(128)
 frontend_kernel(const float *__restrict__ z, const float *__restrict__ eps, const float *__restrict__ meta,
                 float *__restrict__ mu_r, float *__restrict__ std_r, float *__restrict__ lstd_r,
                 float *__restrict__ zhat_nq, __half *__restrict__ a_img, float *__restrict__ wrow,
-                float *__restrict__ margin, int64_t b, int64_t l, int C, int layout, float lv_lo, float lv_hi,
-                int64_t M, int64_t M_pad, float beta, float w_max)
+                float *__restrict__ margin, SegHdr *__restrict__ seg_hdr, uint32_t *__restrict__ rec_cnt, int nseg,
+                int64_t b, int64_t l, int C, int layout, float lv_lo, float lv_hi, int64_t M, int64_t M_pad,
+                float beta, float w_max)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M_pad) return;
@@ -991,7 +988,8 @@ frontend_kernel(const float *__restrict__ z, const float *__restrict__ eps, cons
 #pragma unroll
         for (int k = 0; k < G; ++k) { m[k] = 0.f; s[k] = 1.f; ls[k] = 0.f; }
     }
-    prep_row<G, KPAD>(m, s, ls, meta, beta, w_max, valid, a_img + r * KPAD, wrow + r, margin + r);
+    prep_row<G, KPAD>(m, s, ls, meta, beta, w_max, valid, a_img + r * KPAD, wrow + r, margin + r,
+                      seg_hdr + r * nseg, rec_cnt + r * nseg, nseg);
 }
 
 // Row indices -> the module's output tensors (gaussian.py:153-158): indices [b,l,ncb] / [b,ncb,h,w]
@@ -1073,8 +1071,8 @@ static int run_latent(const gq_codebook *cb, const float *z, const float *eps, i
     TcPlan p = make_plan(cb, M);
     TcWorkspace w = carve(cb, p, lw.tc);
     frontend_kernel<G, KPAD><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
-        z, eps, cb->meta, lw.mu_r, lw.std_r, lw.lstd_r, zhat_nq, w.a_img, w.wrow, w.margin, b, l, C, layout, lv_lo,
-        lv_hi, M, p.M_pad, cb->beta, g_w_max);
+        z, eps, cb->meta, lw.mu_r, lw.std_r, lw.lstd_r, zhat_nq, w.a_img, w.wrow, w.margin, w.seg, w.rec_cnt, p.nseg, b, l, C,
+        layout, lv_lo, lv_hi, M, p.M_pad, cb->beta, g_w_max);
     int rc = check_launch("frontend_kernel");
     if (rc) return rc;
     rc = run_tc<G, KPAD>(cb, lw.mu_r, lw.std_r, lw.lstd_r, M, lw.idx_rows, nullptr, p, w, stats, g_w_max, stream,
