@@ -138,26 +138,48 @@ kl_fwd_kernel(const float *__restrict__ z, const float *__restrict__ eps, float 
         is_last = (prev == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
+    if (is_last) {
+        // the last block to finish folds the per-block partials: thread t takes partials t, t+256, ...
+        // in order, then a fixed shuffle/shared tree -- the same association on every run
         __threadfence();
-        KlPartial t{0.0, 0.0, CUDART_INF_F, -CUDART_INF_F};
-        for (unsigned int k = 0; k < gridDim.x; ++k) {
+        double t_all = 0.0, t_w = 0.0;
+        float t_mn = CUDART_INF_F, t_mx = -CUDART_INF_F;
+        for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) {
             const volatile KlPartial *p = &partials[k];
-            t.s_all += p->s_all;
-            t.s_w += p->s_w;
-            t.mn = fminf(t.mn, p->mn);
-            t.mx = fmaxf(t.mx, p->mx);
+            t_all += p->s_all;
+            t_w += p->s_w;
+            t_mn = fminf(t_mn, p->mn);
+            t_mx = fmaxf(t_mx, p->mx);
         }
-        // kl_loss = lam * sum(w*kl2) / b  (gaussian.py:96-98)
-        out_stats[0] = (float)((double)lam * t.s_w / (double)b);
-        out_stats[1] = (float)(t.s_all / (double)total);
-        out_stats[2] = t.mn;
-        out_stats[3] = t.mx;
-        out_stats[4] = (float)t.s_all;
-        out_stats[5] = (float)t.s_w;
-        out_stats[6] = 0.f;
-        out_stats[7] = 0.f;
-        *done_counter = 0u;  // re-arm for the next launch on this workspace
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            t_all += __shfl_xor_sync(0xffffffffu, t_all, off);
+            t_w += __shfl_xor_sync(0xffffffffu, t_w, off);
+            t_mn = fminf(t_mn, __shfl_xor_sync(0xffffffffu, t_mn, off));
+            t_mx = fmaxf(t_mx, __shfl_xor_sync(0xffffffffu, t_mx, off));
+        }
+        __syncthreads();   // sh_* were read by thread 0 above
+        if (lane == 0) { sh_all[warp] = t_all; sh_w[warp] = t_w; sh_mn[warp] = t_mn; sh_mx[warp] = t_mx; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            KlPartial t{0.0, 0.0, CUDART_INF_F, -CUDART_INF_F};
+            for (int w = 0; w < kKlThreads / 32; ++w) {
+                t.s_all += sh_all[w];
+                t.s_w += sh_w[w];
+                t.mn = fminf(t.mn, sh_mn[w]);
+                t.mx = fmaxf(t.mx, sh_mx[w]);
+            }
+            // kl_loss = lam * sum(w*kl2) / b  (gaussian.py:96-98)
+            out_stats[0] = (float)((double)lam * t.s_w / (double)b);
+            out_stats[1] = (float)(t.s_all / (double)total);
+            out_stats[2] = t.mn;
+            out_stats[3] = t.mx;
+            out_stats[4] = (float)t.s_all;
+            out_stats[5] = (float)t.s_w;
+            out_stats[6] = 0.f;
+            out_stats[7] = 0.f;
+            *done_counter = 0u;  // re-arm for the next launch on this workspace
+        }
     }
 }
 
@@ -180,20 +202,45 @@ kl_bwd_kernel(const float *__restrict__ z, const float *__restrict__ eps, const 
         int64_t zb, zs, ob, os, lvo, row;
         kl_addr(layout, i, l, ncb, C, zb, zs, ob, os, lvo, row);
         const float s = sc * (w ? __ldg(w + row) : 1.0f);
+        float mu[G], lr[G], ep[G], gz[G], gmu[G], glv[G];
+        const bool vec = (layout == GQ_LAYOUT_BLC && ncb == 1 && G % 4 == 0);
+        if (vec) {
+            load_row<G>(z + zb, mu);
+            load_row<G>(z + zb + lvo, lr);
+            if (eps) load_row<G>(eps + ob, ep);
+            if (grad_zhat) load_row<G>(grad_zhat + ob, gz);
+        } else {
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                mu[k] = __ldg(z + zb + k * zs);
+                lr[k] = __ldg(z + zb + lvo + k * zs);
+                if (eps) ep[k] = __ldg(eps + ob + k * os);
+                if (grad_zhat) gz[k] = __ldg(grad_zhat + ob + k * os);
+            }
+        }
 #pragma unroll
         for (int k = 0; k < G; ++k) {
-            float mu = __ldg(z + zb + k * zs);
-            float lr = __ldg(z + zb + lvo + k * zs);
-            float ep = eps ? __ldg(eps + ob + k * os) : 0.f;
-            float gz = grad_zhat ? __ldg(grad_zhat + ob + k * os) : 0.f;
-            float v = fminf(fmaxf(lr, lv_lo), lv_hi);
-            bool inside = (lr >= lv_lo) && (lr <= lv_hi);
-            float var = expf(v);
-            float sd = expf(0.5f * v);
-            float gmu = s * (2.0f * kKlScale) * mu + gz;
-            float glv = inside ? (s * kKlScale * (var - 1.0f) + gz * ep * 0.5f * sd) : 0.f;
-            grad_z[zb + k * zs] = gmu;
-            grad_z[zb + lvo + k * zs] = glv;
+            const float e = eps ? ep[k] : 0.f;
+            const float g_ = grad_zhat ? gz[k] : 0.f;
+            const float v = fminf(fmaxf(lr[k], lv_lo), lv_hi);
+            const bool inside = (lr[k] >= lv_lo) && (lr[k] <= lv_hi);
+            const float var = expf(v);
+            const float sd = expf(0.5f * v);
+            gmu[k] = s * (2.0f * kKlScale) * mu[k] + g_;
+            glv[k] = inside ? (s * kKlScale * (var - 1.0f) + g_ * e * 0.5f * sd) : 0.f;
+        }
+        if (vec) {
+#pragma unroll
+            for (int k = 0; k < G / 4; ++k) {
+                reinterpret_cast<float4 *>(grad_z + zb)[k] = make_float4(gmu[4 * k], gmu[4 * k + 1], gmu[4 * k + 2], gmu[4 * k + 3]);
+                reinterpret_cast<float4 *>(grad_z + zb + lvo)[k] = make_float4(glv[4 * k], glv[4 * k + 1], glv[4 * k + 2], glv[4 * k + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                grad_z[zb + k * zs] = gmu[k];
+                grad_z[zb + lvo + k * zs] = glv[k];
+            }
         }
     }
 }
