@@ -198,10 +198,10 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity)
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware rather than spin
         : "memory");
     return ok != 0;
 }

@@ -77,7 +77,8 @@ constexpr int kStages = 8;           // B ring depth
 constexpr int kAccStages = 3;        // TMEM accumulator stages, round-robin over (tile, row block)
 constexpr int kTmemCols = 512;       // 3 x 128 accumulator columns + the two A operands
 constexpr int kTmemACol = kAccStages * kTileN;
-constexpr int kThreads = 384;        // producer, 2 MMA issuers, TMEM allocator + 8 epilogue warps
+constexpr int kThreads = 640;        // producer, 2 MMA issuers, TMEM allocator + 16 epilogue warps
+constexpr int kHalves = 2;           // each accumulator tile is drained by two warps per lane quarter (64 columns each)
 constexpr int kEpiWarp0 = 4;
 constexpr int kCap = 32;             // chunk records per (row, segment)
 constexpr int kChunk = 32;           // columns per recorded chunk
@@ -102,7 +103,7 @@ struct TcPlan {
     int64_t total_steps; // units * tiles
     int ctas;
     int steps_per_cta;
-    int nseg;            // max CTAs touching one unit
+    int nseg;            // storage segments per row: kHalves x (max CTAs touching one unit)
 };
 
 static TcPlan make_plan_sms(int64_t N, int64_t n_pad, int64_t M, int sms)
@@ -118,7 +119,7 @@ static TcPlan make_plan_sms(int64_t N, int64_t n_pad, int64_t M, int sms)
     p.ctas = (int)imin(sms, imax(1, max_ctas));
     p.steps_per_cta = (int)((p.total_steps + p.ctas - 1) / p.ctas);
     p.ctas = (int)((p.total_steps + p.steps_per_cta - 1) / p.steps_per_cta);
-    p.nseg = (p.tiles + p.steps_per_cta - 1) / p.steps_per_cta + 1;
+    p.nseg = kHalves * ((p.tiles + p.steps_per_cta - 1) / p.steps_per_cta + 1);
     return p;
 }
 
@@ -394,7 +395,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         for (int i = 0; i < kStages; ++i) mbar_init(&bars[kStages + i], 2);                        // empty_b: 2 issuers
         for (int i = 0; i < 2; ++i) mbar_init(&bars[2 * kStages + i], 4);                          // a_full: 4 warps
         for (int i = 0; i < 2 * kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + i], 1);                   // acc_full
-        for (int i = 0; i < 2 * kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + 2 * kAccStages + i], 4);  // acc_empty
+        for (int i = 0; i < 2 * kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + 2 * kAccStages + i], 4 * kHalves);  // acc_empty: 8 warps
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -478,65 +479,85 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         }
     } else if (warp >= kEpiWarp0) {
         // ===== epilogue: TMEM -> registers, running row max, chunk records =====
+        // 16 warps: (row block, column half, lane quarter).  Thread <-> (row, column half): each row is
+        // watched by two threads with independent running maxima / record lists ("storage segments"
+        // 2*piece + half); four epilogue warps per scheduler hide the barrier and TMEM-load latencies.
         const int ew = warp - kEpiWarp0;
-        const int rb = ew >> 2;
+        const int rb = (ew >> 2) & 1;
+        const int half = ew >> 3;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const bool padded = (N % kTileN) != 0;
+        constexpr int kHalfCols = kTileN / kHalves;
         int64_t step = step_begin;
         Piece p;
-        int as = rb;             // this row block consumes every other accumulator use
-        uint32_t cp = 0;         // parity of (own use index / 3) == phase parity of acc_full(as, rb)
-        int pos = 0;
+        // This row block's uses of the accumulator ring visit stages rb, rb+2, rb+4 (mod 3), then repeat.
+        // Three rotating (barrier address, TMEM address, phase parity) triples replace all per-tile
+        // stage arithmetic: the head triple is the current use; after it the parity flips and the
+        // triple moves to the back.  acc_empty(s, rb) sits at a constant offset from acc_full(s, rb).
+        constexpr uint32_t kEmptyOff = 8u * 2u * kAccStages;
+        const int sA = rb, sB = (rb + 2) % kAccStages, sC = (rb + 4) % kAccStages;
+        uint32_t fa = acc_full(sA, rb), fb = acc_full(sB, rb), fc = acc_full(sC, rb);
+        const uint32_t tcol0 = tmem_base + lane_base + (uint32_t)(half * kHalfCols);
+        uint32_t ta = tcol0 + sA * kTileN, tb = tcol0 + sB * kTileN, tc = tcol0 + sC * kTileN;
+        uint32_t pa = 0, pb = 0, pc = 0;
+        int pad_tile;   // pinned in a register (otherwise re-derived from the kernel parameters every tile)
+        asm volatile("mov.b32 %0, %1;" : "=r"(pad_tile) : "r"(padded ? tiles - 1 : -1));
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
             const int64_t row = (int64_t)p.unit * kUnitRows + rb * kBlockRows + q * 32 + lane;
-            // Row operand into tensor memory.  Every MMA of the previous piece that read this row
-            // block's operand has completed: this warp consumed that piece's last accumulator.
-            store_a_rows<KPAD>(tmem_base + lane_base + (uint32_t)(kTmemACol + rb * (KPAD / 2)), a_img + row * KPAD);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(a_full(rb));
+            const int sseg = p.seg * kHalves + half;
+            if (half == 0) {
+                // Row operand into tensor memory.  Every MMA of the previous piece that read this row
+                // block's operand has completed: this warp consumed that piece's last accumulator.
+                store_a_rows<KPAD>(tmem_base + lane_base + (uint32_t)(kTmemACol + rb * (KPAD / 2)), a_img + row * KPAD);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(a_full(rb));
+            }
 
             const float w = wrow[row];
             float runmax = -CUDART_INF_F;
             float thr = (w >= 0.f) ? -CUDART_INF_F : CUDART_INF_F;
             uint32_t cnt = 0;
-            Cand *list = cand + (row * nseg + p.seg) * (int64_t)kCap;
+            Cand *list = cand + (row * nseg + sseg) * (int64_t)kCap;
             for (int t = p.t0; t < p.t1; ++t) {
-                mbar_wait_a(acc_full(as, rb), cp);
+                mbar_wait_a(fa, pa);
                 tc_fence_after();
-                float v[128];
-                tmem_ld_32x128_sync(tmem_base + lane_base + (uint32_t)(as * kTileN), v);
-                // the tile now lives in registers: hand the TMEM stage back before doing any math
+                float v[kHalfCols];
+                tmem_ld_32x64_sync(ta, v);
+                // the half tile now lives in registers: hand the TMEM stage back before doing any math
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_a(acc_empty(as, rb));
-                as += 2;
-                if (as >= kAccStages) as -= kAccStages;
-                if (++pos == 3) { pos = 0; cp ^= 1; }
+                if (lane == 0) mbar_arrive_a(fa + kEmptyOff);
+                {
+                    const uint32_t f_ = fa, t_ = ta, p_ = pa ^ 1u;
+                    fa = fb; fb = fc; fc = f_;
+                    ta = tb; tb = tc; tc = t_;
+                    pa = pb; pb = pc; pc = p_;
+                }
 
                 if constexpr (DUMP) {
                     // debug build only: spill the raw tensor-core scores [M_pad, tiles*128]
-                    float *drow = dump + row * ((int64_t)tiles * kTileN) + (int64_t)t * kTileN;
+                    float *drow = dump + row * ((int64_t)tiles * kTileN) + (int64_t)t * kTileN + half * kHalfCols;
 #pragma unroll
-                    for (int i = 0; i < 128; ++i) drow[i] = v[i];
+                    for (int i = 0; i < kHalfCols; ++i) drow[i] = v[i];
                 }
-                const uint32_t chunk0 = (uint32_t)t * (kTileN / kChunk);
-                if (padded && t == tiles - 1) {
+                const uint32_t chunk0 = (uint32_t)t * (kTileN / kChunk) + (uint32_t)half * (kHalfCols / kChunk);
+                if (t == pad_tile) {
                     // last tile of a codebook that is not a multiple of 128: columns >= N hold the
                     // zero padding rows of the operand image and must not raise the running max
-                    const int n_in_tile = (int)(N - (int64_t)t * kTileN);
+                    const int n_in_half = (int)(N - (int64_t)t * kTileN) - half * kHalfCols;
 #pragma unroll
-                    for (int c = 0; c < kTileN / kChunk; ++c) {
+                    for (int c = 0; c < kHalfCols / kChunk; ++c) {
                         float m = -CUDART_INF_F;
 #pragma unroll
                         for (int i = 0; i < kChunk; ++i)
-                            if (c * kChunk + i < n_in_tile) m = fmaxf(m, v[c * kChunk + i]);
-                        if (m >= thr && c * kChunk < n_in_tile) epi_record(m, chunk0 + c, w, runmax, thr, cnt, list);
+                            if (c * kChunk + i < n_in_half) m = fmaxf(m, v[c * kChunk + i]);
+                        if (m >= thr && c * kChunk < n_in_half) epi_record(m, chunk0 + c, w, runmax, thr, cnt, list);
                     }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < kTileN / kChunk; ++c) {
+                    for (int c = 0; c < kHalfCols / kChunk; ++c) {
                         const float m = chunk_max32(v + c * kChunk);
                         if (m >= thr) epi_record(m, chunk0 + c, w, runmax, thr, cnt, list);
                     }
@@ -545,7 +566,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             // piece done: filter this thread's own records against its final maximum and publish the
             // survivors (typically one or two) in the 64-byte segment summary
             {
-                SegHdr *hp = &seg_hdr[row * nseg + p.seg];
+                SegHdr *hp = &seg_hdr[row * nseg + sseg];
                 uint32_t ns = 0;
                 bool ovf = cnt > (uint32_t)kCap;
                 const float keep = runmax - w;
@@ -560,7 +581,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                 }
                 hp->runmax = runmax;
                 hp->cnt = ovf ? kSegOverflow : ns;
-                rec_cnt[row * nseg + p.seg] = cnt;
+                rec_cnt[row * nseg + sseg] = cnt;
             }
         }
     }
@@ -612,7 +633,7 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
         const bool full = (entry & 0x80000000u) != 0u;   // a segment kept more than kSurv survivors: walk its full list
         const int64_t r = entry & 0x7fffffffu;
         const uint32_t s0 = (uint32_t)(r / kUnitRows) * (uint32_t)tiles;
-        const int npieces = (int)((s0 + (uint32_t)tiles - 1u) / (uint32_t)steps_per_cta) - (int)(s0 / (uint32_t)steps_per_cta) + 1;
+        const int npieces = kHalves * ((int)((s0 + (uint32_t)tiles - 1u) / (uint32_t)steps_per_cta) - (int)(s0 / (uint32_t)steps_per_cta) + 1);
         float gmax = -CUDART_INF_F;
         for (int s = 0; s < npieces; ++s) gmax = fmaxf(gmax, seg_hdr[r * nseg + s].runmax);
         const float thr = gmax - wrow[r];
