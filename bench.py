@@ -69,10 +69,15 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+
+    The sampler process is started before warm-up (it needs a few hundred ms to come up) and runs
+    until the end; `window(t0, t1)` then keeps the samples whose timestamps fall inside the timed
+    region (widened by half a second when the region is shorter than the sampling period)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -87,9 +92,9 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        rows = []
         if self.p is None:
-            return out
+            return rows
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -97,31 +102,31 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        clocks, reasons, mx, power = [], set(), None, []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 8:
+            if len(parts) < 9:
                 continue
             try:
-                clocks.append(float(parts[1]))
-                mx = float(parts[2])
-                power.append(float(parts[3]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[2]), float(parts[3]), float(parts[4]),
+                             [nm for nm, v in zip(self.NAMES, parts[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
-        if clocks:
-            # "under load": samples in the upper half of the observed power range
-            if power and max(power) > min(power):
-                thr = min(power) + 0.5 * (max(power) - min(power))
-                load = [c for c, p in zip(clocks, power) if p >= thr] or clocks
-            else:
-                load = clocks
-            out.update({"sm_mhz": statistics.median(load), "sm_max_mhz": mx, "reasons": sorted(reasons),
-                        "samples": len(clocks), "power_w_max": max(power) if power else None})
+        return rows
+
+    @staticmethod
+    def window(rows, t0, t1):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sel = [r for r in rows if t0 <= r[0] <= t1]
+        if len(sel) < 3:
+            sel = [r for r in rows if t0 - 0.5 <= r[0] <= t1 + 0.5]
+        if not sel:
+            return out
+        reasons = sorted({x for r in sel for x in r[4]})
+        out.update({"sm_mhz": statistics.median(r[1] for r in sel), "sm_max_mhz": sel[-1][2], "reasons": reasons,
+                    "samples": len(sel), "power_w_max": max(r[3] for r in sel)})
         return out
 
 
@@ -196,6 +201,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     L = _lib.lib()
     reg = gq_b200.GaussianQuantRegularizer(format="bchw", n_samples=N_SAMPLES, group=GROUP, backend="cuda").to(dev).eval()
     B = args.batch
@@ -221,14 +228,13 @@ def main():
     torch.cuda.synchronize()
 
     # ---- timed region: device-resident inputs ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     L.gq_profile_enable(1)
     launches0 = gq_b200.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
+    t_epoch0 = time.time()
     for k in range(args.steps):
         ev[k][0].record()
         step(pool[k % pool_n])
@@ -236,13 +242,13 @@ def main():
     torch.cuda.synchronize()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    t_epoch1 = time.time()
     launches = gq_b200.launch_count() - launches0
     L.gq_profile_enable(0)
     import ctypes
     tot = ctypes.c_double(0.0)
     cnt = ctypes.c_int(0)
     L.gq_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
-    clocks = sampler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     # the steps run back to back on one stream: first-start -> last-stop is the honest span
     span_ms = ev[0][0].elapsed_time(ev[-1][1])
@@ -270,6 +276,8 @@ def main():
     torch.cuda.synchronize()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+
+    clocks = ClockSampler.window(sampler.stop(), t_epoch0, t_epoch1)
 
     # ---- max over ranks ----
     t = torch.tensor([total_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)

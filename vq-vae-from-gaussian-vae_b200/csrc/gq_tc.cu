@@ -492,9 +492,10 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         int64_t step = step_begin;
         Piece p;
         // This row block's uses of the accumulator ring visit stages rb, rb+2, rb+4 (mod 3), then repeat.
-        // Three rotating (barrier address, TMEM address, phase parity) triples replace all per-tile
-        // stage arithmetic: the head triple is the current use; after it the parity flips and the
-        // triple moves to the back.  acc_empty(s, rb) sits at a constant offset from acc_full(s, rb).
+        // Three rotating (barrier address, TMEM address, phase parity) triples replace all per-tile stage
+        // arithmetic: the head triple is the current use; after it the parity flips and the triple
+        // moves to the back (register moves on the FMA pipe; the ALU pipe is the scarce one here).
+        // acc_empty(s, rb) sits at a constant offset from acc_full(s, rb).
         constexpr uint32_t kEmptyOff = 8u * 2u * kAccStages;
         const int sA = rb, sB = (rb + 2) % kAccStages, sC = (rb + 4) % kAccStages;
         uint32_t fa = acc_full(sA, rb), fb = acc_full(sB, rb), fc = acc_full(sC, rb);
@@ -519,15 +520,19 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             float runmax = -CUDART_INF_F;
             float thr = (w >= 0.f) ? -CUDART_INF_F : CUDART_INF_F;
             uint32_t cnt = 0;
-            Cand *list = cand + (row * nseg + sseg) * (int64_t)kCap;
-            for (int t = p.t0; t < p.t1; ++t) {
+            const uint32_t seg_index = (uint32_t)(row * nseg + sseg);   // < 2^32, checked on the host
+            uint32_t chunk0 = (uint32_t)p.t0 * (kTileN / kChunk) + (uint32_t)half * (kHalfCols / kChunk);
+            int t = p.t0;
+
+            // one accumulator use: wait, pull the warp's 32x64 half tile into registers, release the
+            // TMEM stage at once (tcgen05.wait::ld is warp-collective, so lane 0 may arrive for the
+            // warp), then reduce two 32-column chunks against the running maximum
+            while (t < p.t1) {
                 mbar_wait_a(fa, pa);
                 tc_fence_after();
                 float v[kHalfCols];
                 tmem_ld_32x64_sync(ta, v);
-                // the half tile now lives in registers: hand the TMEM stage back before doing any math
                 tc_fence_before();
-                __syncwarp();
                 if (lane == 0) mbar_arrive_a(fa + kEmptyOff);
                 {
                     const uint32_t f_ = fa, t_ = ta, p_ = pa ^ 1u;
@@ -535,14 +540,12 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                     ta = tb; tb = tc; tc = t_;
                     pa = pb; pb = pc; pc = p_;
                 }
-
                 if constexpr (DUMP) {
                     // debug build only: spill the raw tensor-core scores [M_pad, tiles*128]
                     float *drow = dump + row * ((int64_t)tiles * kTileN) + (int64_t)t * kTileN + half * kHalfCols;
 #pragma unroll
                     for (int i = 0; i < kHalfCols; ++i) drow[i] = v[i];
                 }
-                const uint32_t chunk0 = (uint32_t)t * (kTileN / kChunk) + (uint32_t)half * (kHalfCols / kChunk);
                 if (t == pad_tile) {
                     // last tile of a codebook that is not a multiple of 128: columns >= N hold the
                     // zero padding rows of the operand image and must not raise the running max
@@ -553,20 +556,24 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 #pragma unroll
                         for (int i = 0; i < kChunk; ++i)
                             if (c * kChunk + i < n_in_half) m = fmaxf(m, v[c * kChunk + i]);
-                        if (m >= thr && c * kChunk < n_in_half) epi_record(m, chunk0 + c, w, runmax, thr, cnt, list);
+                        if (m >= thr && c * kChunk < n_in_half) epi_record(m, chunk0 + c, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
                     }
                 } else {
-#pragma unroll
-                    for (int c = 0; c < kHalfCols / kChunk; ++c) {
-                        const float m = chunk_max32(v + c * kChunk);
-                        if (m >= thr) epi_record(m, chunk0 + c, w, runmax, thr, cnt, list);
+                    const float m0 = chunk_max32(v);
+                    const float m1 = chunk_max32(v + kChunk);
+                    if (fmaxf(m0, m1) >= thr) {
+                        if (m0 >= thr) epi_record(m0, chunk0, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
+                        if (m1 >= thr) epi_record(m1, chunk0 + 1, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
                     }
                 }
+                chunk0 += kTileN / kChunk;
+                ++t;
             }
+            Cand *list = cand + (int64_t)seg_index * kCap;
             // piece done: filter this thread's own records against its final maximum and publish the
             // survivors (typically one or two) in the 64-byte segment summary
             {
-                SegHdr *hp = &seg_hdr[row * nseg + sseg];
+                SegHdr *hp = &seg_hdr[seg_index];
                 uint32_t ns = 0;
                 bool ovf = cnt > (uint32_t)kCap;
                 const float keep = runmax - w;
@@ -581,7 +588,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                 }
                 hp->runmax = runmax;
                 hp->cnt = ovf ? kSegOverflow : ns;
-                rec_cnt[row * nseg + sseg] = cnt;
+                rec_cnt[seg_index] = cnt;
             }
         }
     }
@@ -1112,7 +1119,8 @@ int launch_quantize_latent(const gq_codebook *cb, const float *z, const float *e
     if (C % cb->g) { set_error("channels %d not divisible by group %d", C, cb->g); return GQ_ERR_INVALID; }
     const int64_t M = b * l * (C / cb->g);
     if (M == 0) return GQ_OK;
-    if (M >= ((int64_t)1 << 31) || (M / kUnitRows + 1) * (cb->n_pad / kTileN) >= ((int64_t)1 << 31)) {
+    if (M >= ((int64_t)1 << 31) || (M / kUnitRows + 1) * (cb->n_pad / kTileN) >= ((int64_t)1 << 31) ||
+        (M + kUnitRows) * make_plan(cb, M).nseg >= ((int64_t)1 << 32)) {
         set_error("problem too large: rows x codebook tiles must stay below 2^31");
         return GQ_ERR_INVALID;
     }
@@ -1146,7 +1154,8 @@ int launch_quantize_tc(const gq_codebook *cb, const float *mu, const float *std,
                        cudaStream_t stream)
 {
     if (M == 0) return GQ_OK;
-    if (M >= ((int64_t)1 << 31) || (M / kUnitRows + 1) * (cb->n_pad / kTileN) >= ((int64_t)1 << 31)) {
+    if (M >= ((int64_t)1 << 31) || (M / kUnitRows + 1) * (cb->n_pad / kTileN) >= ((int64_t)1 << 31) ||
+        (M + kUnitRows) * make_plan(cb, M).nseg >= ((int64_t)1 << 32)) {
         set_error("problem too large: rows x codebook tiles must stay below 2^31");
         return GQ_ERR_INVALID;
     }
