@@ -43,6 +43,12 @@ def num_threads() -> int:
     return int(lib().gq_oracle_num_threads())
 
 
+def set_num_threads(n: int = 0) -> int:
+    """Use n OpenMP threads (0 = every online core); returns the count now in effect."""
+    lib().gq_oracle_set_num_threads(ctypes.c_int(n))
+    return num_threads()
+
+
 def _f32(a) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 

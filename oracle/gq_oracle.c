@@ -9,7 +9,7 @@
  * Parity status: PINNED.  The reference ships no golden vectors, so the
  * restatement is pinned against outputs of the unmodified reference module imported from
  * /root/reference in the build container (tests/golden/make_golden.py wrote
- * tests/golden/*.npz; tests/test_oracle_golden.py replays them bit-for-bit).
+ * tests/golden/NAME.npz; tests/test_oracle_golden.py replays them bit-for-bit).
  *
  * Every function cites the reference lines it restates (paths relative to the
  * reference checkout).  All arithmetic is IEEE binary32 with no contraction
@@ -33,6 +33,18 @@
 static const float C0F = (float)0.9189385332046727;
 
 int gq_oracle_version(void) { return 1; }
+
+/* Use n host threads (n <= 0: every online core).  torchrun exports OMP_NUM_THREADS=1 to its
+ * workers; the CPU baseline has to override that to use the whole host. */
+void gq_oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n <= 0) n = omp_get_num_procs();
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 int gq_oracle_num_threads(void)
 {

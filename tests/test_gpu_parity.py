@@ -362,3 +362,61 @@ def test_module_eval_rng_parity_with_reference_call(gq):
     torch.manual_seed(78)
     want_t = rearrange(mu + torch.randn_like(mu) * std, "b (h w) c -> b c h w", h=8)
     torch.testing.assert_close(zhat_t, want_t, rtol=1e-6, atol=1e-6)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,g,M", [(100, 16, 33), (31, 8, 5), (128, 16, 256), (4096, 1, 64), (4096, 2, 129), (2048, 32, 70),
+                                   (65536, 16, 3), (129, 4, 1000)])
+def test_quantize_odd_shapes_vs_oracle(gq, N, g, M):
+    """Tiny / ragged codebooks (N < tile, N % 32 != 0), every supported group, M not a multiple of 256."""
+    rng = np.random.RandomState(N + g + M)
+    cb = rng.randn(N, g).astype(np.float32)
+    nlp = oracle.normal_log_prob(cb)
+    h = gq.Codebook(dev(cb), dev(nlp), 1.0)
+    mu = (rng.randn(M, g) * 0.8).astype(np.float32)
+    std = np.exp(0.5 * (-1.2 + 0.4 * rng.randn(M, g))).astype(np.float32)
+    lstd = torch.from_numpy(std).log().numpy()
+    idx, zhat = gq.quantize_rows(h, dev(mu), dev(std), dev(lstd))
+    o_idx, o_zhat, _, gap = oracle.quantize(mu, std, lstd, cb, nlp)
+    bad = np.nonzero(idx.cpu().numpy() != o_idx)[0]
+    assert len(bad) == 0, f"mismatch rows {bad[:5]} gaps {gap[bad][:5]}"
+    assert np.array_equal(zhat.cpu().numpy(), o_zhat)
+
+
+def test_quantize_degenerate_rows(gq):
+    """Rows the search cannot certify must still come out as the exact scan would give them:
+    tiny variances (window too wide), huge variances, duplicate codewords (exact ties -> first
+    index), and rows with non-finite inputs (must not crash or poison their neighbours)."""
+    N, g = 4096, 16
+    cb, nlp, h = big_codebook(gq, N, g)
+    rng = np.random.RandomState(9)
+    M = 300
+    mu = (rng.randn(M, g) * 0.8).astype(np.float32)
+    std = np.exp(0.5 * (-1.2 + 0.4 * rng.randn(M, g))).astype(np.float32)
+    std[0:10] = 1e-4                      # logvar ~ -18: ill-conditioned expansion
+    std[10:20] = 50.0                     # a > 0: score grows with |x|
+    mu[20] = cb[7].numpy()                # sits on a codeword
+    std[20] = 0.2
+    mu[30:32] = np.nan                    # garbage in
+    std[32] = np.inf
+    lstd = torch.from_numpy(std).log().numpy()
+    idx, zhat = gq.quantize_rows(h, dev(mu), dev(std), dev(lstd))
+    idx2, _ = gq.quantize_rows(h, dev(mu), dev(std), dev(lstd), exact=True)
+    ok = np.ones(M, bool)
+    ok[30:33] = False                     # NaN/inf rows: only require a valid index
+    o_idx, _, _, _ = oracle.quantize(mu[ok], std[ok], lstd[ok], cb.numpy(), nlp.numpy())
+    got = idx.cpu().numpy()
+    assert np.array_equal(got[ok], o_idx)
+    assert np.array_equal(idx2.cpu().numpy()[ok], o_idx)
+    assert got[20] == 7
+    assert ((got >= 0) & (got < N)).all()
+    # duplicate codewords: exact ties resolve to the first index on every path
+    cb2 = cb.numpy().copy()
+    cb2[100] = cb2[5]
+    cb2[3000] = cb2[5]
+    nlp2 = oracle.normal_log_prob(cb2)
+    h2 = gq.Codebook(dev(cb2), dev(nlp2), 1.0)
+    mu_t = np.repeat(cb2[5][None], 4, 0) + 0.01
+    std_t = np.full((4, g), 0.3, np.float32)
+    it, _ = gq.quantize_rows(h2, dev(mu_t), dev(std_t), dev(np.log(std_t)))
+    assert (it.cpu().numpy() == 5).all()
