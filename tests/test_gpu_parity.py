@@ -272,6 +272,64 @@ def test_kl_full_size_vs_oracle(gq):
     assert torch.equal(zhat.cpu(), mu)     # eps=None -> zhat = mu
 
 
+@pytest.mark.parametrize("fmt,b,l,C,g", [
+    ("blc", 3, 37, 16, 16), ("blc", 3, 37, 16, 8), ("blc", 2, 50, 16, 4), ("blc", 2, 9, 16, 2),     # C=16 quad-lane kernels + generic
+    ("bchw", 3, 36, 16, 16), ("bchw", 2, 64, 16, 8), ("bchw", 2, 20, 16, 4), ("bchw", 2, 20, 16, 1),  # 4-token kernels + generic
+    ("bchw", 2, 35, 16, 16), ("blc", 2, 33, 8, 8), ("bchw", 2, 12, 32, 16), ("blc", 1, 7, 32, 32),   # l%4 != 0, C != 16
+])
+def test_kl_kernel_variants_vs_torch_autograd(gq, fmt, b, l, C, g):
+    """Every dispatch arm of gq_kl_fwd / gq_kl_bwd against the reference's torch expression
+    (gaussian.py:76-98) differentiated by autograd on the same device; fp32 tolerance 1e-5."""
+    gen = torch.Generator().manual_seed(l * 7 + g)
+    ncb = C // g
+    if fmt == "bchw":
+        z = torch.cat([torch.randn(b, C, l, 1, generator=gen), -1.0 + 1.5 * torch.randn(b, C, l, 1, generator=gen)], 1)
+        z[0, C:, 0, 0] = 25.0
+        z[0, C:, 1, 0] = -40.0
+        eps = torch.randn(b, C, l, 1, generator=gen)
+        wz = torch.randn(b, C, l, 1, generator=gen)
+        layout = gq.ops.GQ_LAYOUT_BCHW
+    else:
+        z = torch.cat([torch.randn(b, l, C, generator=gen), -1.0 + 1.5 * torch.randn(b, l, C, generator=gen)], 2)
+        z[0, 0, C:] = 25.0
+        z[0, 1, C:] = -40.0
+        eps = torch.randn(b, l, C, generator=gen)
+        wz = torch.randn(b, l, C, generator=gen)
+        layout = gq.ops.GQ_LAYOUT_BLC
+    target = 0.7213 * g * 1.2
+    lam, lam_min, lam_max = 1.3, 0.6, 2.5
+    z1 = z.cuda().requires_grad_(True)
+    zhat, kl, stats = gq.kl_penalty(z1, eps.cuda(), g, layout, (-30.0, 20.0), target, 0.5, lam, lam_min, lam_max)
+    (0.3 * kl + (zhat * wz.cuda()).sum()).backward()
+    # torch restatement of the reference lines
+    z2 = z.cuda().double().requires_grad_(True)
+    zz = z2.reshape(b, 2 * C, l).permute(0, 2, 1) if fmt == "bchw" else z2
+    mu, lv = zz.chunk(2, dim=2)
+    lv = lv.clamp(-30.0, 20.0)
+    std = torch.exp(0.5 * lv)
+    e = eps.cuda().double()
+    e = e.reshape(b, C, l).permute(0, 2, 1) if fmt == "bchw" else e
+    zh = mu + e * std
+    kl2 = 1.4426 * 0.5 * (mu ** 2 + lv.exp() - 1.0 - lv)
+    kl2 = kl2.reshape(b, l, g, ncb).sum(2)
+    ge = (kl2 > target + 0.5).double() * lam_max
+    eq = ((kl2 <= target + 0.5) & (kl2 >= target - 0.5)).double()
+    le = (kl2 < target - 0.5).double() * lam_min
+    kl_ref = lam * ((ge + eq + le) * kl2).sum([1, 2]).mean()
+    w2 = wz.cuda().double()
+    w2 = w2.reshape(b, C, l).permute(0, 2, 1) if fmt == "bchw" else w2
+    (0.3 * kl_ref + (zh * w2).sum()).backward()
+    st = stats.cpu().numpy()
+    assert float(kl) == pytest.approx(float(kl_ref), rel=1e-5)
+    assert st[1] == pytest.approx(float(kl2.mean()), rel=1e-5)
+    assert st[2] == pytest.approx(float(kl2.min()), rel=1e-5, abs=1e-6)
+    assert st[3] == pytest.approx(float(kl2.max()), rel=1e-5)
+    zh_ref = zh.permute(0, 2, 1).reshape(b, C, l, 1) if fmt == "bchw" else zh
+    np.testing.assert_allclose(zhat.detach().cpu().numpy(), zh_ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-5)
+    gref = z2.grad.cpu().numpy()
+    np.testing.assert_allclose(z1.grad.cpu().numpy(), gref, rtol=1e-4, atol=1e-5 * np.abs(gref).max())
+
+
 # ---- GaussianQuantRegularizer2 ("next" row of SURVEY 8f) ----------------------------------------------------
 @pytest.mark.parametrize("name", ["gq2_bchw_dim16", "gq2_blc_dim8"])
 def test_gq2_golden(gq, name):

@@ -440,6 +440,26 @@ dequant_kernel(const int64_t *__restrict__ idx, const float *__restrict__ cb, fl
 {
     const int64_t total = b * l * ncb;
     const int C = ncb * G;
+    // Warm the L2 with the codebook as one linear sweep (128-byte lines) before the random gather:
+    // a cold table otherwise costs one scattered 64-byte DRAM access per row.
+    if (total >= N) {
+        const int64_t lines = (N * G * 4 + 127) / 128;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < lines; i += (int64_t)gridDim.x * blockDim.x)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(cb + i * 32));
+    }
+    if (layout == GQ_LAYOUT_BLC && ncb == 1 && G % 4 == 0) {
+        // G/4 lanes per row, one 16-byte quarter each: loads and stores are both lane-contiguous
+        constexpr int Q = (G >= 4) ? G / 4 : 1;
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total * Q; e += (int64_t)gridDim.x * blockDim.x) {
+            int64_t id = __ldg(idx + e / Q);
+            if (id < 0 || id >= N) {
+                if (err_flag) *err_flag = 1;
+                id = 0;
+            }
+            reinterpret_cast<float4 *>(out)[e] = __ldg(reinterpret_cast<const float4 *>(cb) + id * Q + (e % Q));
+        }
+        return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         int64_t bi, t;
@@ -483,7 +503,9 @@ int launch_dequant(const gq_codebook *cb, const int64_t *idx, float *out, int64_
 {
     const int64_t total = b * l * ncb;
     if (total == 0) return GQ_OK;
-    int blocks = (int)imin((total + 255) / 256, 148 * 16);
+    int64_t items = total;
+    if (layout == GQ_LAYOUT_BLC && ncb == 1 && cb->g % 4 == 0) items = total * (cb->g / 4);
+    int blocks = (int)imin((items + 255) / 256, 148 * 16);
 #define GQ_DQ(GG) dequant_kernel<GG><<<blocks, 256, 0, stream>>>(idx, cb->cb, out, b, l, ncb, cb->N, layout, err_flag)
     switch (cb->g) {
     case 1: GQ_DQ(1); break;
