@@ -135,25 +135,36 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
 }
 
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = lane base + i).
+// Asynchronous: v[] is defined only after tmem_ld_wait_32(v) (or tmem_ld_wait()).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32])
 {
-    uint32_t r[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]),
+          "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),
+          "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
         : "r"(taddr)
         : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait()
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// tcgen05.wait::ld that names the 32 destination registers of an earlier tmem_ld_32x32 as in/out
+// operands: every later use of v[] depends on this statement, so the compiler cannot schedule a
+// consumer between the asynchronous load and the wait (or reuse the registers in between).
+__device__ __forceinline__ void tmem_ld_wait_32(float (&v)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                   "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+                   "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
+                   "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :
+                 : "memory");
 }
 
 
@@ -192,6 +203,12 @@ __device__ __forceinline__ void tmem_ld_32x128_sync(uint32_t taddr, float (&v)[1
     for (int i = 0; i < 128; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Generic-proxy shared-memory writes made visible to the async proxy (tensor core, bulk copies).
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // ---- u32-address mbarrier forms (addresses computed once, outside the hot loops) -----------
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity)
 {
@@ -208,6 +225,33 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity)
 {
     while (!mbar_try_wait_a(bar, parity)) { }
+}
+// Early probe / late wait pair.  A satisfied mbarrier wait still costs ~100 cycles of latency, and
+// the warp issues in order, so the probe's answer must not be touched until independent work has
+// been issued behind it.  The answer therefore lives in a PTX predicate that is declared once per
+// kernel (mbar_probe_declare, in the entry block) and is only read by mbar_probe_wait_a: no
+// C++-visible value exists that the compiler could materialise early.
+__device__ __forceinline__ void mbar_probe_declare()
+{
+    asm volatile(".reg .pred gq_rdy;\n\tsetp.ne.u32 gq_rdy, 0, 0;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_probe_a(uint32_t bar, uint32_t parity)
+{
+    asm volatile("mbarrier.test_wait.parity.shared::cta.b64 gq_rdy, [%0], %1;" ::"r"(bar), "r"(parity) : "memory");
+}
+// Blocks until the phase is complete; free when the earlier probe already saw it.
+__device__ __forceinline__ void mbar_probe_wait_a(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        "@gq_rdy bra.uni GQ_PROBE_DONE;\n"
+        "GQ_PROBE_RETRY:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 gq_rdy, [%0], %1, %2;\n\t"
+        "@!gq_rdy bra GQ_PROBE_RETRY;\n"
+        "GQ_PROBE_DONE:\n\t"
+        "}"
+        ::"r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
 }
 
 // Wait on two barriers with both probes in flight before either result is consumed (a satisfied

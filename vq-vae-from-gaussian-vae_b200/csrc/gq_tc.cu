@@ -5,29 +5,31 @@
 // gather the winning codeword.  The reference materialises an [M, N] score matrix in HBM;
 // here it lives only in tensor memory.
 //
-// Pipeline (three launches + one optional fallback launch, all on the caller's stream):
+// Pipeline (all launches on the caller's stream):
 //   1. rows_prep_kernel   per row: A[r,:] = s_r*[beta/2 - 1/(2v) | mu/v] as fp16, a RIGOROUS
 //                         window W_r bounding twice the worst-case |fp16 tensor-core score -
 //                         reference fp32 score| gap, and the (much smaller) margin of the fp32
 //                         prefilter used by the rescoring kernel.
-//   2. quantize_tc_kernel persistent, warp-specialised: bulk-async-copy (TMA engine) streams
-//                         the prepared [x^2 | x] codebook image through a shared-memory ring,
-//                         one thread issues tcgen05.mma (fp16 x fp16 -> fp32, M=128, N=128,
-//                         K=2g) with the ROW operand resident in TENSOR MEMORY (so each MMA
-//                         reads only the codebook tile from shared memory) into three TMEM
-//                         accumulators, eight epilogue warps pull tiles with tcgen05.ld (the
-//                         whole 32x128 tile of a warp into registers, so the TMEM stage is
-//                         released before any math) and keep a running row maximum with
-//                         FMNMX3; a 32-column chunk whose maximum comes within W_r of the
-//                         running maximum is recorded as (max, chunk id).
+//   2. quantize_tc_kernel persistent, warp-specialised, 640 threads: a producer warp streams the
+//                         prepared [x^2 | x] codebook image through an 8-slot shared-memory ring
+//                         (bulk async copies, TMA engine); one issuer warp per 128-row block
+//                         issues tcgen05.mma (fp16 x fp16 -> fp32, M=128, N=128, K=2g, both
+//                         operands from shared memory: the row operand is written there once
+//                         per work unit) into that row block's two private TMEM accumulator
+//                         stages (4 x 128 columns = all of tensor memory); sixteen epilogue
+//                         warps pull 32x64 half tiles with tcgen05.ld, hand the stage back
+//                         before any math, and keep a running row maximum with FMNMX3; a
+//                         32-column chunk whose maximum comes within W_r of the running
+//                         maximum is recorded as (max, chunk id); per-piece survivors are
+//                         compacted into a 64-byte segment summary.
 //   3. rescore_kernel     one warp per row: drop chunk records below (final max - W_r), score
 //                         the 32 codewords of every surviving chunk (lane = codeword) with an
 //                         fp32 FMA form; if exactly one codeword lies within the prefilter
-//                         margin of the best it is the answer, otherwise the contenders are
-//                         re-scored in the reference's exact fp32 op order (first-max
-//                         tie-break).  Rows whose window is too wide, that overflow their
-//                         list, or that contain non-finite values go to
-//   4. quantize_exact_kernel (gq_kernels.cu) through a device-side row list.
+//                         margin of the best it is the answer, otherwise the row goes to
+//   4. settle_kernel      (a few percent of the rows) which re-scores the contenders in the
+//                         reference's exact fp32 op order (first-max tie-break).  Rows whose
+//                         window is too wide or that contain non-finite values go to
+//   5. exact_sliced_kernel (gq_kernels.cu), an exact-order scan, through a device-side row list.
 //
 // Why the result is exactly the reference argmax: with E_r >= |G~[n]/s - (S_ref[n] - Q_r)| for
 // all n (Q_r constant in n), the reference argmax n* satisfies
@@ -74,12 +76,14 @@ constexpr int kTileN = 128;          // codewords per B tile / MMA N
 constexpr int kBlockRows = 128;      // rows per MMA (M)
 constexpr int kUnitRows = 256;       // rows per CTA work unit (two row blocks)
 constexpr int kStages = 8;           // B ring depth
-constexpr int kAccStages = 3;        // TMEM accumulator stages, round-robin over (tile, row block)
-constexpr int kTmemCols = 512;       // 3 x 128 accumulator columns + the two A operands
-constexpr int kTmemACol = kAccStages * kTileN;
-constexpr int kThreads = 640;        // producer, 2 MMA issuers, TMEM allocator + 16 epilogue warps
+constexpr int kAccStages = 4;        // TMEM accumulator stages: two private ones per row block (rb, rb + 2)
+constexpr int kTmemCols = 512;       // 4 x 128 accumulator columns (the row operands live in shared memory)
+constexpr int kThreads = 640;        // 16 epilogue warps, producer, 2 MMA issuers, TMEM allocator
 constexpr int kHalves = 2;           // each accumulator tile is drained by two warps per lane quarter (64 columns each)
-constexpr int kEpiWarp0 = 4;
+// Warp roles: 16 epilogue warps, then the service warps (bulk-copy producer, one MMA issuer per row
+// block, TMEM allocator).  20 warps is the most the register file holds at 96 registers per thread.
+constexpr int kEpiWarp0 = 0;         // epilogue warps 0..15
+constexpr int kProducerWarp = 16, kIssuerWarp0 = 17, kAllocWarp = 18, kIssuerWarp1 = 19;
 constexpr int kCap = 32;             // chunk records per (row, segment)
 constexpr int kChunk = 32;           // columns per recorded chunk
 constexpr int kMinStepsPerCta = 8;
@@ -299,9 +303,12 @@ template <int KPAD>
 struct TcSmem {
     static constexpr int kBTileBytes = kTileN * KPAD * 2;
     static constexpr int kBOff = 0;
-    static constexpr int kBarOff = kBOff + kStages * kBTileBytes;
-    // barriers: full_b[kStages], empty_b[kStages], a_full[2], acc_full[3][2], acc_empty[3][2]
-    static constexpr int kNumBars = 2 * kStages + 2 + 4 * kAccStages;
+    // row operand of each of the two row blocks, same canonical K-major core-matrix layout as a B tile
+    static constexpr int kABytes = kBlockRows * KPAD * 2;
+    static constexpr int kAOff = kBOff + kStages * kBTileBytes;
+    static constexpr int kBarOff = kAOff + 2 * kABytes;
+    // barriers: full_b[kStages], empty_b[kStages], a_full[2], acc_full[kAccStages], acc_empty[kAccStages]
+    static constexpr int kNumBars = 2 * kStages + 2 + 2 * kAccStages;
     static constexpr int kSlotOff = kBarOff + kNumBars * 8;
     static constexpr int kBytes = kSlotOff + 16;
 };
@@ -324,12 +331,25 @@ __device__ __forceinline__ bool next_piece(int64_t &step, int64_t end, int tiles
 // Maximum of 32 consecutive columns: 14 FMNMX3 + 2 FMNMX.
 __device__ __forceinline__ float chunk_max32(const float *v)
 {
+#ifdef GQ_EXP_NOREDUCE
+    return fmaxf(v[0], v[31]);   // timing experiment only (results are wrong): how fast is the pipeline without the reduction?
+#endif
     float a0 = max3(v[0], v[1], v[2]), a1 = max3(v[3], v[4], v[5]), a2 = max3(v[6], v[7], v[8]);
     float a3 = max3(v[9], v[10], v[11]), a4 = max3(v[12], v[13], v[14]), a5 = max3(v[15], v[16], v[17]);
     float a6 = max3(v[18], v[19], v[20]), a7 = max3(v[21], v[22], v[23]), a8 = max3(v[24], v[25], v[26]);
     float a9 = max3(v[27], v[28], v[29]), a10 = fmaxf(v[30], v[31]);
     float b0 = max3(a0, a1, a2), b1 = max3(a3, a4, a5), b2 = max3(a6, a7, a8), b3 = fmaxf(a9, a10);
     return fmaxf(max3(b0, b1, b2), b3);
+}
+
+// Same over the first n (<= 32, possibly <= 0) registers only; -inf when n <= 0.
+__device__ __forceinline__ float chunk_max32_masked(const float *v, int n)
+{
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i)
+        if (i < n) m = fmaxf(m, v[i]);
+    return m;
 }
 
 // Slow path (~10 times per row over 2048 chunks): raise the running max / threshold and record
@@ -342,21 +362,34 @@ __device__ __forceinline__ void epi_record(float m, uint32_t chunk, float w, flo
     ++cnt;
 }
 
+// One row of the row-operand image (KPAD fp16, row-major in global memory) into the shared-memory
+// operand of its row block: canonical K-major no-swizzle layout, core matrix = 8 rows x 16 bytes,
+// K-adjacent core matrices 128 bytes apart, 8-row groups (KPAD / 8) * 128 bytes apart -- the layout
+// of a codebook tile, so both descriptors share LBO / SBO.
 template <int KPAD>
-__device__ __forceinline__ void store_a_rows(uint32_t taddr, const __half *__restrict__ a_row)
+__device__ __forceinline__ void store_a_row_smem(uint32_t a_smem, int r, const __half *__restrict__ a_row)
 {
-    constexpr int NW = KPAD / 2;   // 32-bit words per row: two fp16 K-elements per TMEM column
-    uint32_t r[NW];
+    const uint32_t base = a_smem + (uint32_t)(r >> 3) * (uint32_t)((KPAD / 8) * 128) + (uint32_t)(r & 7) * 16u;
 #pragma unroll
-    for (int c = 0; c < NW / 4; ++c) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(a_row) + c);
-        r[4 * c + 0] = q.x; r[4 * c + 1] = q.y; r[4 * c + 2] = q.z; r[4 * c + 3] = q.w;
+    for (int j = 0; j < KPAD / 8; ++j) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(a_row) + j);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)j * 128u), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
     }
-    if constexpr (NW == 8) tmem_st_32x8(taddr, r);
-    else if constexpr (NW == 16) tmem_st_32x16(taddr, r);
-    else tmem_st_32x32(taddr, r);
-    tmem_st_wait();
 }
+
+#ifdef GQ_TC_TRACE
+// diagnostic build only (scripts/tc_prof.py): clock64 timeline of CTA 0, iterations [kTraceFrom, +kTraceN)
+constexpr int kTraceFrom = 300, kTraceN = 24;
+__device__ unsigned int g_tc_trace[32 * kTraceN * 4];
+#define GQ_TRACE_DECL() uint32_t tr_it_ = 0; const long long tr_t0_ = clock64()
+#define GQ_TRACE(slot) do { if (cta == 0 && lane == 0 && tr_it_ >= kTraceFrom && tr_it_ < kTraceFrom + kTraceN) \
+        g_tc_trace[(warp * kTraceN + (tr_it_ - kTraceFrom)) * 4 + (slot)] = (unsigned int)(clock64() - tr_t0_); } while (0)
+#define GQ_TRACE_NEXT() (++tr_it_)
+#else
+#define GQ_TRACE_DECL()
+#define GQ_TRACE(slot)
+#define GQ_TRACE_NEXT()
+#endif
 
 template <int KPAD, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -375,12 +408,11 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     auto full_b = [&](int i) { return bar_base + 8u * i; };
     auto empty_b = [&](int i) { return bar_base + 8u * (kStages + i); };
     auto a_full = [&](int i) { return bar_base + 8u * (2 * kStages + i); };                      // per row block
-    // Accumulator barriers are per (stage, row block): the three stages are shared round-robin by
-    // the two row blocks, so a per-stage barrier would be waited on by each party only every other
-    // phase, which a parity wait cannot tell apart.  acc_full(s, rb): MMA of row block rb into stage
-    // s complete.  acc_empty(s, rb): the epilogue warps of row block rb have drained stage s.
-    auto acc_full = [&](int st, int rb_) { return bar_base + 8u * (2 * kStages + 2 + 2 * st + rb_); };
-    auto acc_empty = [&](int st, int rb_) { return bar_base + 8u * (2 * kStages + 2 + 2 * kAccStages + 2 * st + rb_); };
+    // Accumulator stages are private to a row block (rb owns stages rb and rb + 2): a classic double
+    // buffer per consumer group.  acc_full(s): the MMA into stage s is complete.  acc_empty(s): the
+    // eight epilogue warps of the owning row block have pulled stage s into registers.
+    auto acc_full = [&](int st) { return bar_base + 8u * (2 * kStages + 2 + st); };
+    auto acc_empty = [&](int st) { return bar_base + 8u * (2 * kStages + 2 + kAccStages + st); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kSlotOff);
 
     const int warp = threadIdx.x >> 5;
@@ -388,17 +420,19 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     const int cta = blockIdx.x;
     const int64_t step_begin = (int64_t)cta * steps_per_cta;
     const int64_t step_end = imin(step_begin + steps_per_cta, total_steps);
+    mbar_probe_declare();
+    GQ_TRACE_DECL();
 
-    if (warp == 1 && lane == 0) {
+    if (warp == kIssuerWarp0 && lane == 0) {
         uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kBarOff);
         for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);                                  // full_b
         for (int i = 0; i < kStages; ++i) mbar_init(&bars[kStages + i], 2);                        // empty_b: 2 issuers
         for (int i = 0; i < 2; ++i) mbar_init(&bars[2 * kStages + i], 4);                          // a_full: 4 warps
-        for (int i = 0; i < 2 * kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + i], 1);                   // acc_full
-        for (int i = 0; i < 2 * kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + 2 * kAccStages + i], 4 * kHalves);  // acc_empty: 8 warps
+        for (int i = 0; i < kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + i], 1);                           // acc_full
+        for (int i = 0; i < kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + kAccStages + i], 4 * kHalves);     // acc_empty: 8 warps
         fence_mbar_init();
     }
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
     }
@@ -407,7 +441,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == kProducerWarp) {
         // ===== producer: bulk async copies (TMA engine) of codebook tiles =====
         // The whole warp runs the loop (warp-uniform control flow keeps addresses on the uniform
         // datapath); one elected lane arms the barrier and issues the copy.
@@ -419,69 +453,79 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             for (int t = p.t0; t < p.t1; ++t) {
                 mbar_wait_a(empty_b(stage), phase ^ 1);
                 if (elect_one()) {
+#ifdef GQ_EXP_HALFCOPY
+                    // timing experiment only (results are wrong): every second tile is not copied at all
+                    if (t & 1) mbar_arrive_a(full_b(stage)); else {
+#endif
                     mbar_expect_tx_a(full_b(stage), L::kBTileBytes);
                     bulk_g2s_a(smem_base + L::kBOff + stage * L::kBTileBytes,
                                reinterpret_cast<const char *>(b_img) + (int64_t)t * L::kBTileBytes,
                                L::kBTileBytes, full_b(stage));
+#ifdef GQ_EXP_HALFCOPY
+                    }
+#endif
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 || warp == 3) {
-        // ===== MMA issuers: warp 1 drives row block 0, warp 3 row block 1.  Each warp waits
-        // together (warp-uniform control flow), one elected lane issues to the tensor core. =====
-        const int rb = warp >> 1;
+    } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
+        // ===== MMA issuers, one per row block.  The whole warp runs the loop (warp-uniform control flow
+        // keeps the addresses on the uniform datapath), one elected lane issues to the tensor core. =====
+        const int rb = (warp == kIssuerWarp1) ? 1 : 0;
         constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockRows, kTileN);
         constexpr uint32_t kLbo = 128;              // K-adjacent core matrices
         constexpr uint32_t kSbo = (KPAD / 8) * 128; // next 8-row group
         // descriptor words: everything but the 14-bit start address is loop invariant
         constexpr uint32_t desc_hi = ((kSbo >> 4) & 0x3FFFu) | (1u << 14);           // SBO, version = 1
         const uint32_t desc_lo0 = (((smem_base + L::kBOff) >> 4) & 0x3FFFu) | (((kLbo >> 4) & 0x3FFFu) << 16);
-        const uint32_t a_t = tmem_base + (uint32_t)(kTmemACol + rb * (KPAD / 2));
+        const uint32_t adesc_lo0 = (((smem_base + L::kAOff + rb * L::kABytes) >> 4) & 0x3FFFu) | (((kLbo >> 4) & 0x3FFFu) << 16);
         int64_t step = step_begin;
         Piece p;
         int stage = 0;
         uint32_t phase = 0;
-        // Use q = 2*i + rb of the accumulator ring goes to stage q % 3; this row block's i-th use is
-        // its (i/3)-th visit of that stage (cycle parity cp).  The stage was last drained by the
-        // OTHER row block (use q-3); that is its (i/3)-th drain of the stage if the other row block
-        // is the stage's first user (stage parity != rb), else its (i/3 - 1)-th.
-        int as = rb;         // stage of the next use
-        uint32_t cp = 0;     // parity of i / 3
-        int pos = 0;         // i % 3
+        int sub = 0;          // which of this row block's two accumulator stages the next use takes
+        uint32_t ep = 1;      // parity to wait for on acc_empty: passes at once on the first visit of a stage
         int pi = 0;
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
             mbar_wait_a(a_full(rb), pi & 1);
             tc_fence_after();
             for (int t = p.t0; t < p.t1; ++t) {
-                const uint32_t empty_par = ((as & 1) == rb) ? (cp ^ 1) : cp;
-                mbar_wait2_a(full_b(stage), phase, acc_empty(as, rb ^ 1), empty_par);
+                const int as = rb + 2 * sub;
+                GQ_TRACE(0);
+                mbar_wait2_a(full_b(stage), phase, acc_empty(as), ep);
+                GQ_TRACE(1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d = tmem_base + (uint32_t)(as * kTileN);
                     const uint32_t desc_lo = desc_lo0 + (uint32_t)stage * (L::kBTileBytes >> 4);
 #pragma unroll
                     for (int j = 0; j < KPAD / 16; ++j) {
+                        // one K = 16 slice = two K-adjacent core matrices = 256 bytes in either operand
+                        const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(adesc_lo0 + j * 16);
                         const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo + j * 16);
-                        umma_f16_ts(d, a_t + j * 8, bd, idesc, j > 0 ? 1u : 0u);
+                        umma_f16_ss(d, ad, bd, idesc, j > 0 ? 1u : 0u);
                     }
-                    umma_commit_a(acc_full(as, rb));
+                    GQ_TRACE(2);
+                    umma_commit_a(acc_full(as));
                     umma_commit_a(empty_b(stage));   // 2 arrivals (one per row block) free the B slot
                 }
                 __syncwarp();
-                as += 2;
-                if (as >= kAccStages) as -= kAccStages;
-                if (++pos == 3) { pos = 0; cp ^= 1; }
+                GQ_TRACE(3);
+                GQ_TRACE_NEXT();
+                sub ^= 1;
+                if (sub == 0) ep ^= 1;
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
             ++pi;
         }
-    } else if (warp >= kEpiWarp0) {
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 16) {
         // ===== epilogue: TMEM -> registers, running row max, chunk records =====
         // 16 warps: (row block, column half, lane quarter).  Thread <-> (row, column half): each row is
         // watched by two threads with independent running maxima / record lists ("storage segments"
         // 2*piece + half); four epilogue warps per scheduler hide the barrier and TMEM-load latencies.
+        // (Tried and measured slower, see DESIGN.md 4.4: the two warps of a row taking alternate tiles
+        // instead of column halves; a software-pipelined loop of 32-column loads; four issuer warps.)
         const int ew = warp - kEpiWarp0;
         const int rb = (ew >> 2) & 1;
         const int half = ew >> 3;
@@ -491,27 +535,26 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         constexpr int kHalfCols = kTileN / kHalves;
         int64_t step = step_begin;
         Piece p;
-        // This row block's uses of the accumulator ring visit stages rb, rb+2, rb+4 (mod 3), then repeat.
-        // Three rotating (barrier address, TMEM address, phase parity) triples replace all per-tile stage
-        // arithmetic: the head triple is the current use; after it the parity flips and the triple
-        // moves to the back (register moves on the FMA pipe; the ALU pipe is the scarce one here).
-        // acc_empty(s, rb) sits at a constant offset from acc_full(s, rb).
-        constexpr uint32_t kEmptyOff = 8u * 2u * kAccStages;
-        const int sA = rb, sB = (rb + 2) % kAccStages, sC = (rb + 4) % kAccStages;
-        uint32_t fa = acc_full(sA, rb), fb = acc_full(sB, rb), fc = acc_full(sC, rb);
+        // This row block's uses alternate between its two private stages rb and rb + 2.  Two
+        // (barrier address, TMEM address, phase parity) triples swap places after every use, the used
+        // one with its parity flipped (register moves on the FMA pipe; the ALU pipe is the scarce one
+        // here).  acc_empty(s) sits at a constant offset from acc_full(s).
+        constexpr uint32_t kEmptyOff = 8u * kAccStages;
+        uint32_t fa = acc_full(rb), fb = acc_full(rb + 2);
         const uint32_t tcol0 = tmem_base + lane_base + (uint32_t)(half * kHalfCols);
-        uint32_t ta = tcol0 + sA * kTileN, tb = tcol0 + sB * kTileN, tc = tcol0 + sC * kTileN;
-        uint32_t pa = 0, pb = 0, pc = 0;
+        uint32_t ta = tcol0 + rb * kTileN, tb = tcol0 + (rb + 2) * kTileN;
+        uint32_t pa = 0, pb = 0;
         int pad_tile;   // pinned in a register (otherwise re-derived from the kernel parameters every tile)
         asm volatile("mov.b32 %0, %1;" : "=r"(pad_tile) : "r"(padded ? tiles - 1 : -1));
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
             const int64_t row = (int64_t)p.unit * kUnitRows + rb * kBlockRows + q * 32 + lane;
             const int sseg = p.seg * kHalves + half;
             if (half == 0) {
-                // Row operand into tensor memory.  Every MMA of the previous piece that read this row
+                // Row operand into shared memory.  Every MMA of the previous piece that read this row
                 // block's operand has completed: this warp consumed that piece's last accumulator.
-                store_a_rows<KPAD>(tmem_base + lane_base + (uint32_t)(kTmemACol + rb * (KPAD / 2)), a_img + row * KPAD);
-                tc_fence_before();
+                // The tensor core reads through the async proxy: fence before signalling.
+                store_a_row_smem<KPAD>(smem_base + L::kAOff + rb * L::kABytes, q * 32 + lane, a_img + row * KPAD);
+                fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_a(a_full(rb));
             }
@@ -519,6 +562,9 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             const float w = wrow[row];
             float runmax = -CUDART_INF_F;
             float thr = (w >= 0.f) ? -CUDART_INF_F : CUDART_INF_F;
+#ifdef GQ_EXP_NOREC
+            thr = CUDART_INF_F;   // timing experiment only: the record path is never taken (results are wrong)
+#endif
             uint32_t cnt = 0;
             const uint32_t seg_index = (uint32_t)(row * nseg + sseg);   // < 2^32, checked on the host
             uint32_t chunk0 = (uint32_t)p.t0 * (kTileN / kChunk) + (uint32_t)half * (kHalfCols / kChunk);
@@ -528,17 +574,20 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             // TMEM stage at once (tcgen05.wait::ld is warp-collective, so lane 0 may arrive for the
             // warp), then reduce two 32-column chunks against the running maximum
             while (t < p.t1) {
-                mbar_wait_a(fa, pa);
+                GQ_TRACE(0);
+                mbar_probe_wait_a(fa, pa);
+                GQ_TRACE(1);
                 tc_fence_after();
                 float v[kHalfCols];
                 tmem_ld_32x64_sync(ta, v);
+                GQ_TRACE(2);
                 tc_fence_before();
                 if (lane == 0) mbar_arrive_a(fa + kEmptyOff);
                 {
                     const uint32_t f_ = fa, t_ = ta, p_ = pa ^ 1u;
-                    fa = fb; fb = fc; fc = f_;
-                    ta = tb; tb = tc; tc = t_;
-                    pa = pb; pb = pc; pc = p_;
+                    fa = fb; fb = f_;
+                    ta = tb; tb = t_;
+                    pa = pb; pb = p_;
                 }
                 if constexpr (DUMP) {
                     // debug build only: spill the raw tensor-core scores [M_pad, tiles*128]
@@ -550,16 +599,19 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                     // last tile of a codebook that is not a multiple of 128: columns >= N hold the
                     // zero padding rows of the operand image and must not raise the running max
                     const int n_in_half = (int)(N - (int64_t)t * kTileN) - half * kHalfCols;
+                    mbar_probe_a(fa, pa);
 #pragma unroll
                     for (int c = 0; c < kHalfCols / kChunk; ++c) {
-                        float m = -CUDART_INF_F;
-#pragma unroll
-                        for (int i = 0; i < kChunk; ++i)
-                            if (c * kChunk + i < n_in_half) m = fmaxf(m, v[c * kChunk + i]);
+                        const float m = chunk_max32_masked(v + c * kChunk, n_in_half - c * kChunk);
                         if (m >= thr && c * kChunk < n_in_half) epi_record(m, chunk0 + c, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
                     }
                 } else {
+                    // Probe the NEXT use's barrier half way through the reduction: the answer (a predicate
+                    // only mbar_probe_wait_a reads) is there by the time the loop comes around, so a
+                    // satisfied wait costs nothing instead of ~100 idle cycles per tile.  Once true it
+                    // stays true: the phase cannot advance again before this warp drains the stage.
                     const float m0 = chunk_max32(v);
+                    mbar_probe_a(fa, pa);
                     const float m1 = chunk_max32(v + kChunk);
                     if (fmaxf(m0, m1) >= thr) {
                         if (m0 >= thr) epi_record(m0, chunk0, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
@@ -568,6 +620,8 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                 }
                 chunk0 += kTileN / kChunk;
                 ++t;
+                GQ_TRACE(3);
+                GQ_TRACE_NEXT();
             }
             Cand *list = cand + (int64_t)seg_index * kCap;
             // piece done: filter this thread's own records against its final maximum and publish the
@@ -595,7 +649,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
@@ -1205,3 +1259,11 @@ void debug_plan(int64_t N, int64_t M, int sms, int64_t *out)
 }
 
 }  // namespace gq
+
+#ifdef GQ_TC_TRACE
+extern "C" int gq_debug_tc_trace(unsigned int *out)
+{
+    cudaMemcpyFromSymbol(out, gq::g_tc_trace, sizeof(unsigned int) * 32 * gq::kTraceN * 4);
+    return gq::kTraceN;
+}
+#endif

@@ -6,11 +6,14 @@ expected symbols the import fails loudly (the product path is CUDA-only).
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32,
                     c_uint64, c_void_p)
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libgq_b200.so"
+# GQ_B200_LIB points the binding at another build of the same library (instrumented diagnostic
+# builds, scripts/tc_prof.py); it is still a CUDA build of this ABI, never a fallback.
+LIB_PATH = Path(os.environ.get("GQ_B200_LIB") or (Path(__file__).resolve().parent / "libgq_b200.so"))
 
 GQ_OK = 0
 GQ_LAYOUT_BLC = 0
