@@ -535,15 +535,14 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         constexpr int kHalfCols = kTileN / kHalves;
         int64_t step = step_begin;
         Piece p;
-        // This row block's uses alternate between its two private stages rb and rb + 2.  Two
-        // (barrier address, TMEM address, phase parity) triples swap places after every use, the used
-        // one with its parity flipped (register moves on the FMA pipe; the ALU pipe is the scarce one
-        // here).  acc_empty(s) sits at a constant offset from acc_full(s).
+        // This row block's two private stages A = rb and B = rb + 2: barrier address, TMEM address and
+        // the phase parity of the next use.  acc_empty(s) sits at a constant offset from acc_full(s).
         constexpr uint32_t kEmptyOff = 8u * kAccStages;
-        uint32_t fa = acc_full(rb), fb = acc_full(rb + 2);
+        const uint32_t fa = acc_full(rb), fb = acc_full(rb + 2);
         const uint32_t tcol0 = tmem_base + lane_base + (uint32_t)(half * kHalfCols);
-        uint32_t ta = tcol0 + rb * kTileN, tb = tcol0 + (rb + 2) * kTileN;
+        const uint32_t ta = tcol0 + rb * kTileN, tb = tcol0 + (rb + 2) * kTileN;
         uint32_t pa = 0, pb = 0;
+        int cur = 0;   // 0: the next use takes stage A, 1: stage B
         int pad_tile;   // pinned in a register (otherwise re-derived from the kernel parameters every tile)
         asm volatile("mov.b32 %0, %1;" : "=r"(pad_tile) : "r"(padded ? tiles - 1 : -1));
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
@@ -570,36 +569,33 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             uint32_t chunk0 = (uint32_t)p.t0 * (kTileN / kChunk) + (uint32_t)half * (kHalfCols / kChunk);
             int t = p.t0;
 
-            // one accumulator use: wait, pull the warp's 32x64 half tile into registers, release the
+            // One accumulator use: wait, pull the warp's 32x64 half tile into registers, release the
             // TMEM stage at once (tcgen05.wait::ld is warp-collective, so lane 0 may arrive for the
-            // warp), then reduce two 32-column chunks against the running maximum
-            while (t < p.t1) {
+            // warp), then reduce two 32-column chunks against the running maximum.  `nbar/npar` name
+            // the barrier of the use after this one (the row block's other stage).
+            auto use_tile = [&](const uint32_t fbar, const uint32_t taddr, uint32_t &par, const uint32_t nbar,
+                                const uint32_t npar, const bool pad) {
                 GQ_TRACE(0);
-                mbar_probe_wait_a(fa, pa);
+                mbar_probe_wait_a(fbar, par);
                 GQ_TRACE(1);
                 tc_fence_after();
                 float v[kHalfCols];
-                tmem_ld_32x64_sync(ta, v);
+                tmem_ld_32x64_sync(taddr, v);
                 GQ_TRACE(2);
                 tc_fence_before();
-                if (lane == 0) mbar_arrive_a(fa + kEmptyOff);
-                {
-                    const uint32_t f_ = fa, t_ = ta, p_ = pa ^ 1u;
-                    fa = fb; fb = f_;
-                    ta = tb; tb = t_;
-                    pa = pb; pb = p_;
-                }
+                if (lane == 0) mbar_arrive_a(fbar + kEmptyOff);
+                par ^= 1u;
                 if constexpr (DUMP) {
                     // debug build only: spill the raw tensor-core scores [M_pad, tiles*128]
                     float *drow = dump + row * ((int64_t)tiles * kTileN) + (int64_t)t * kTileN + half * kHalfCols;
 #pragma unroll
                     for (int i = 0; i < kHalfCols; ++i) drow[i] = v[i];
                 }
-                if (t == pad_tile) {
+                if (pad) {
                     // last tile of a codebook that is not a multiple of 128: columns >= N hold the
                     // zero padding rows of the operand image and must not raise the running max
                     const int n_in_half = (int)(N - (int64_t)t * kTileN) - half * kHalfCols;
-                    mbar_probe_a(fa, pa);
+                    mbar_probe_a(nbar, npar);
 #pragma unroll
                     for (int c = 0; c < kHalfCols / kChunk; ++c) {
                         const float m = chunk_max32_masked(v + c * kChunk, n_in_half - c * kChunk);
@@ -607,11 +603,11 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                     }
                 } else {
                     // Probe the NEXT use's barrier half way through the reduction: the answer (a predicate
-                    // only mbar_probe_wait_a reads) is there by the time the loop comes around, so a
+                    // only mbar_probe_wait_a reads) is there by the time the next use starts, so a
                     // satisfied wait costs nothing instead of ~100 idle cycles per tile.  Once true it
                     // stays true: the phase cannot advance again before this warp drains the stage.
                     const float m0 = chunk_max32(v);
-                    mbar_probe_a(fa, pa);
+                    mbar_probe_a(nbar, npar);
                     const float m1 = chunk_max32(v + kChunk);
                     if (fmaxf(m0, m1) >= thr) {
                         if (m0 >= thr) epi_record(m0, chunk0, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
@@ -622,6 +618,23 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                 ++t;
                 GQ_TRACE(3);
                 GQ_TRACE_NEXT();
+            };
+            // The row block's uses alternate between its stages A = rb and B = rb + 2 (`cur` says which
+            // comes next and carries over from piece to piece).  The loop is unrolled over one A/B pair:
+            // no per-tile stage bookkeeping, half the loop branches (taken branches cost ~20 cycles of
+            // latency each, and this loop's serial latency is what bounds the kernel).  A padded last
+            // tile (pad_tile = tiles - 1, so it can only end a piece) is peeled off.
+            const bool has_pad = pad_tile >= p.t0 && pad_tile < p.t1;
+            const int t_fast = has_pad ? p.t1 - 1 : p.t1;
+            if (cur && t < t_fast) { use_tile(fb, tb, pb, fa, pa, false); cur = 0; }
+            while (t + 1 < t_fast) {
+                use_tile(fa, ta, pa, fb, pb, false);
+                use_tile(fb, tb, pb, fa, pa, false);
+            }
+            if (t < t_fast) { use_tile(fa, ta, pa, fb, pb, false); cur = 1; }
+            if (has_pad) {
+                if (cur) { use_tile(fb, tb, pb, fa, pa, true); cur = 0; }
+                else { use_tile(fa, ta, pa, fb, pb, true); cur = 1; }
             }
             Cand *list = cand + (int64_t)seg_index * kCap;
             // piece done: filter this thread's own records against its final maximum and publish the
