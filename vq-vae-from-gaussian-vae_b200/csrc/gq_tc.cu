@@ -78,12 +78,16 @@ constexpr int kUnitRows = 256;       // rows per CTA work unit (two row blocks)
 constexpr int kStages = 8;           // B ring depth
 constexpr int kAccStages = 4;        // TMEM accumulator stages: two private ones per row block (rb, rb + 2)
 constexpr int kTmemCols = 512;       // 4 x 128 accumulator columns (the row operands live in shared memory)
-constexpr int kThreads = 640;        // 16 epilogue warps, producer, 2 MMA issuers, TMEM allocator
-constexpr int kHalves = 2;           // each accumulator tile is drained by two warps per lane quarter (64 columns each)
+#ifndef GQ_EPI_HALVES
+#define GQ_EPI_HALVES 2
+#endif
+constexpr int kHalves = GQ_EPI_HALVES;   // warps per lane quarter draining one accumulator tile (128 / kHalves columns each)
+constexpr int kNumEpiWarps = 8 * kHalves;
+constexpr int kThreads = (kNumEpiWarps + 4) * 32;   // epilogue warps, producer, 2 MMA issuers, TMEM allocator
 // Warp roles: 16 epilogue warps, then the service warps (bulk-copy producer, one MMA issuer per row
 // block, TMEM allocator).  20 warps is the most the register file holds at 96 registers per thread.
 constexpr int kEpiWarp0 = 0;         // epilogue warps 0..15
-constexpr int kProducerWarp = 16, kIssuerWarp0 = 17, kAllocWarp = 18, kIssuerWarp1 = 19;
+constexpr int kProducerWarp = kNumEpiWarps, kIssuerWarp0 = kNumEpiWarps + 1, kAllocWarp = kNumEpiWarps + 2, kIssuerWarp1 = kNumEpiWarps + 3;
 constexpr int kCap = 32;             // chunk records per (row, segment)
 constexpr int kChunk = 32;           // columns per recorded chunk
 constexpr int kMinStepsPerCta = 8;
@@ -328,6 +332,9 @@ __device__ __forceinline__ bool next_piece(int64_t &step, int64_t end, int tiles
     return true;
 }
 
+__device__ __forceinline__ void tmem_ld_cols_sync(uint32_t taddr, float (&v)[64]) { tmem_ld_32x64_sync(taddr, v); }
+__device__ __forceinline__ void tmem_ld_cols_sync(uint32_t taddr, float (&v)[128]) { tmem_ld_32x128_sync(taddr, v); }
+
 // Maximum of 32 consecutive columns: 14 FMNMX3 + 2 FMNMX.
 __device__ __forceinline__ float chunk_max32(const float *v)
 {
@@ -519,7 +526,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             }
             ++pi;
         }
-    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 16) {
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kNumEpiWarps) {
         // ===== epilogue: TMEM -> registers, running row max, chunk records =====
         // 16 warps: (row block, column half, lane quarter).  Thread <-> (row, column half): each row is
         // watched by two threads with independent running maxima / record lists ("storage segments"
@@ -580,7 +587,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                 GQ_TRACE(1);
                 tc_fence_after();
                 float v[kHalfCols];
-                tmem_ld_32x64_sync(taddr, v);
+                tmem_ld_cols_sync(taddr, v);
                 GQ_TRACE(2);
                 tc_fence_before();
                 if (lane == 0) mbar_arrive_a(fbar + kEmptyOff);
@@ -606,12 +613,20 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                     // only mbar_probe_wait_a reads) is there by the time the next use starts, so a
                     // satisfied wait costs nothing instead of ~100 idle cycles per tile.  Once true it
                     // stays true: the phase cannot advance again before this warp drains the stage.
-                    const float m0 = chunk_max32(v);
-                    mbar_probe_a(nbar, npar);
-                    const float m1 = chunk_max32(v + kChunk);
-                    if (fmaxf(m0, m1) >= thr) {
-                        if (m0 >= thr) epi_record(m0, chunk0, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
-                        if (m1 >= thr) epi_record(m1, chunk0 + 1, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
+                    constexpr int kC = kHalfCols / kChunk;
+                    float m[kC];
+#pragma unroll
+                    for (int c = 0; c < kC; ++c) {
+                        m[c] = chunk_max32(v + c * kChunk);
+                        if (c == kC / 2 - 1) mbar_probe_a(nbar, npar);
+                    }
+                    float mm = m[0];
+#pragma unroll
+                    for (int c = 1; c < kC; ++c) mm = fmaxf(mm, m[c]);
+                    if (mm >= thr) {
+#pragma unroll
+                        for (int c = 0; c < kC; ++c)
+                            if (m[c] >= thr) epi_record(m[c], chunk0 + c, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
                     }
                 }
                 chunk0 += kTileN / kChunk;
