@@ -700,6 +700,38 @@ __device__ __forceinline__ float prefilter_score(const float (&x)[G], const floa
     return a2;
 }
 
+// The same with the row's mu and 1/(2 var) read from shared memory (16-byte broadcast loads) instead of
+// 2 G registers: identical operation order, hence identical values; lets four blocks share an SM.
+template <int G>
+__device__ __forceinline__ float prefilter_score_smem(const float (&x)[G], const float *__restrict__ m,
+                                                      const float *__restrict__ ri, float hb)
+{
+    float a2 = 0.f;
+    if constexpr (G % 4 == 0) {
+#pragma unroll
+        for (int k4 = 0; k4 < G / 4; ++k4) {
+            const float4 mm = reinterpret_cast<const float4 *>(m)[k4];
+            const float4 rr = reinterpret_cast<const float4 *>(ri)[k4];
+            const float mv[4] = {mm.x, mm.y, mm.z, mm.w}, rv[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xv = x[4 * k4 + j];
+                const float d = xv - mv[j];
+                a2 = fmaf(-d * d, rv[j], a2);
+                a2 = fmaf(hb * xv, xv, a2);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const float d = x[k] - m[k];
+            a2 = fmaf(-d * d, ri[k], a2);
+            a2 = fmaf(hb * x[k], x[k], a2);
+        }
+    }
+    return a2;
+}
+
 constexpr int kMaxChunks = 64;   // surviving chunks one row may carry into the rescoring (else: exact scan)
 
 // Rows whose fp32 prefilter left more than one contender (a few percent): one warp per listed row
@@ -801,7 +833,7 @@ __device__ __forceinline__ RowIn fetch_row(int64_t r, int lane, const float *__r
 // second and last round.  Plans with more than 8 segments per row (tiny M, huge N) send every row to
 // settle_kernel instead.
 template <int G>
-__global__ void __launch_bounds__(kRescoreWarps * 32, (G <= 16) ? 3 : 1)
+__global__ void __launch_bounds__(kRescoreWarps * 32, (G <= 16) ? 4 : 1)
 rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
                const float *__restrict__ cb, const float *__restrict__ wrow, const float *__restrict__ margin_row,
                const SegHdr *__restrict__ seg_hdr, int64_t M, int64_t N, int nseg, float beta,
@@ -879,19 +911,6 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                 __syncwarp();
                 if (nchunks == 0) verdict = 3;
                 else {
-                    float m[G], ri[G];
-                    if constexpr (G % 4 == 0) {
-#pragma unroll
-                        for (int k = 0; k < G / 4; ++k) {
-                            const float4 a = reinterpret_cast<const float4 *>(&s_par[wib][0][0])[k];
-                            const float4 c = reinterpret_cast<const float4 *>(&s_par[wib][1][0])[k];
-                            m[4 * k] = a.x; m[4 * k + 1] = a.y; m[4 * k + 2] = a.z; m[4 * k + 3] = a.w;
-                            ri[4 * k] = c.x; ri[4 * k + 1] = c.y; ri[4 * k + 2] = c.z; ri[4 * k + 3] = c.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < G; ++k) { m[k] = s_par[wib][0][k]; ri[k] = s_par[wib][1][k]; }
-                    }
                     // fp32 FMA prefilter over the surviving chunks: per-lane best and runner-up
                     float a_best = -CUDART_INF_F, a_second = -CUDART_INF_F;
                     int n_best = 0;
@@ -901,7 +920,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                         if (n0 < N) {
                             float x0[G];
                             load_row<G>(cb + n0 * G, x0);
-                            const float a2 = prefilter_score<G>(x0, m, ri, hb);
+                            const float a2 = prefilter_score_smem<G>(x0, &s_par[wib][0][0], &s_par[wib][1][0], hb);
                             if (a2 > a_best) { a_second = a_best; a_best = a2; n_best = (int)n0; }
                             else if (a2 > a_second) a_second = a2;
                         }
