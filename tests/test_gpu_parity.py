@@ -441,6 +441,25 @@ def test_quantize_odd_shapes_vs_oracle(gq, N, g, M):
     assert np.array_equal(zhat.cpu().numpy(), o_zhat)
 
 
+@pytest.mark.parametrize("N,g,M", [(5000, 16, 40037), (3001, 8, 25000), (65536, 16, 1500)])
+def test_quantize_many_units_ragged_vs_oracle(gq, N, g, M):
+    """Stream-K plans with many row units, pieces that start and end mid-codebook (odd and even
+    piece lengths exercise both accumulator stages at a piece boundary), a padded last tile
+    (N % 128 != 0) at the end of every unit, and a ragged last unit (M % 256 != 0)."""
+    rng = np.random.RandomState(N % 1000 + g + M % 1000)
+    cb = rng.randn(N, g).astype(np.float32)
+    nlp = oracle.normal_log_prob(cb)
+    h = gq.Codebook(dev(cb), dev(nlp), 1.0)
+    mu = (rng.randn(M, g) * 0.8).astype(np.float32)
+    std = np.exp(0.5 * (-1.2 + 0.4 * rng.randn(M, g))).astype(np.float32)
+    lstd = torch.from_numpy(std).log().numpy()
+    idx, zhat = gq.quantize_rows(h, dev(mu), dev(std), dev(lstd))
+    o_idx, o_zhat, _, gap = oracle.quantize(mu, std, lstd, cb, nlp)
+    bad = np.nonzero(idx.cpu().numpy() != o_idx)[0]
+    assert len(bad) == 0, f"{len(bad)} mismatching rows, first {bad[:5]} gaps {gap[bad][:5]}"
+    assert np.array_equal(zhat.cpu().numpy(), o_zhat)
+
+
 def test_quantize_degenerate_rows(gq):
     """Rows the search cannot certify must still come out as the exact scan would give them:
     tiny variances (window too wide), huge variances, duplicate codewords (exact ties -> first
