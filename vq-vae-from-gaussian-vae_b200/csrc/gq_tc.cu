@@ -573,14 +573,13 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 #endif
             uint32_t cnt = 0;
             const uint32_t seg_index = (uint32_t)(row * nseg + sseg);   // < 2^32, checked on the host
-            uint32_t chunk0 = (uint32_t)p.t0 * (kTileN / kChunk) + (uint32_t)half * (kHalfCols / kChunk);
             int t = p.t0;
 
             // One accumulator use: wait, pull the warp's 32x64 half tile into registers, release the
             // TMEM stage at once (tcgen05.wait::ld is warp-collective, so lane 0 may arrive for the
             // warp), then reduce two 32-column chunks against the running maximum.  `nbar/npar` name
             // the barrier of the use after this one (the row block's other stage).
-            auto use_tile = [&](const uint32_t fbar, const uint32_t taddr, uint32_t &par, const uint32_t nbar,
+            auto use_tile = [&](const uint32_t fbar, const uint32_t taddr, const uint32_t par, const uint32_t nbar,
                                 const uint32_t npar, const bool pad) {
                 GQ_TRACE(0);
                 mbar_probe_wait_a(fbar, par);
@@ -591,7 +590,6 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                 GQ_TRACE(2);
                 tc_fence_before();
                 if (lane == 0) mbar_arrive_a(fbar + kEmptyOff);
-                par ^= 1u;
                 if constexpr (DUMP) {
                     // debug build only: spill the raw tensor-core scores [M_pad, tiles*128]
                     float *drow = dump + row * ((int64_t)tiles * kTileN) + (int64_t)t * kTileN + half * kHalfCols;
@@ -606,7 +604,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 #pragma unroll
                     for (int c = 0; c < kHalfCols / kChunk; ++c) {
                         const float m = chunk_max32_masked(v + c * kChunk, n_in_half - c * kChunk);
-                        if (m >= thr && c * kChunk < n_in_half) epi_record(m, chunk0 + c, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
+                        if (m >= thr && c * kChunk < n_in_half) epi_record(m, (uint32_t)t * (kTileN / kChunk) + (uint32_t)(half * (kHalfCols / kChunk) + c), w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
                     }
                 } else {
                     // Probe the NEXT use's barrier half way through the reduction: the answer (a predicate
@@ -626,10 +624,9 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                     if (mm >= thr) {
 #pragma unroll
                         for (int c = 0; c < kC; ++c)
-                            if (m[c] >= thr) epi_record(m[c], chunk0 + c, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
+                            if (m[c] >= thr) epi_record(m[c], (uint32_t)t * (kTileN / kChunk) + (uint32_t)(half * (kHalfCols / kChunk) + c), w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
                     }
                 }
-                chunk0 += kTileN / kChunk;
                 ++t;
                 GQ_TRACE(3);
                 GQ_TRACE_NEXT();
@@ -641,21 +638,26 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
             // tile (pad_tile = tiles - 1, so it can only end a piece) is peeled off.
             const bool has_pad = pad_tile >= p.t0 && pad_tile < p.t1;
             const int t_fast = has_pad ? p.t1 - 1 : p.t1;
-            if (cur && t < t_fast) { use_tile(fb, tb, pb, fa, pa, false); cur = 0; }
+            // (a use of stage X flips X's parity; the "next" parity handed to the probe is the other
+            // stage's current one.  Over two A/B pairs both parities return to where they started, so
+            // the main loop carries no parity updates at all.)
+            if (cur && t < t_fast) { use_tile(fb, tb, pb, fa, pa, false); pb ^= 1u; cur = 0; }
             while (t + 3 < t_fast) {   // two A/B pairs per trip: measured 3 % faster than one
                 use_tile(fa, ta, pa, fb, pb, false);
-                use_tile(fb, tb, pb, fa, pa, false);
-                use_tile(fa, ta, pa, fb, pb, false);
-                use_tile(fb, tb, pb, fa, pa, false);
+                use_tile(fb, tb, pb, fa, pa ^ 1u, false);
+                use_tile(fa, ta, pa ^ 1u, fb, pb ^ 1u, false);
+                use_tile(fb, tb, pb ^ 1u, fa, pa, false);
             }
             while (t + 1 < t_fast) {
                 use_tile(fa, ta, pa, fb, pb, false);
+                pa ^= 1u;
                 use_tile(fb, tb, pb, fa, pa, false);
+                pb ^= 1u;
             }
-            if (t < t_fast) { use_tile(fa, ta, pa, fb, pb, false); cur = 1; }
+            if (t < t_fast) { use_tile(fa, ta, pa, fb, pb, false); pa ^= 1u; cur = 1; }
             if (has_pad) {
-                if (cur) { use_tile(fb, tb, pb, fa, pa, true); cur = 0; }
-                else { use_tile(fa, ta, pa, fb, pb, true); cur = 1; }
+                if (cur) { use_tile(fb, tb, pb, fa, pa, true); pb ^= 1u; cur = 0; }
+                else { use_tile(fa, ta, pa, fb, pb, true); pa ^= 1u; cur = 1; }
             }
             Cand *list = cand + (int64_t)seg_index * kCap;
             // piece done: filter this thread's own records against its final maximum and publish the
