@@ -22,6 +22,11 @@
  *   gq_quantize_exact    same semantics, CUDA-core exact-order scan (anchor / fallback)
  *   gq_dequant           pit/quantization/gaussian.py:162-178
  *   gq_kl_fwd/_bwd       pit/quantization/gaussian.py:76-98 (+ autograd of the same)
+ *   gq_index_histogram   eval.py:127,152-154 (all_hist += torch.histogram(indices, range(0, N)))
+ *   gq_usage_entropy     eval.py:137-141 (cal_ent: codebook usage and entropy of the histogram)
+ *   gq_pack_indices / gq_unpack_indices / gq_dequant_packed
+ *                        no reference counterpart: the reference ships int64 indices
+ *                        (gaussian.py:138,159); opt-in 16/32-bit stream, dequant as gaussian.py:162-178
  *
  * Row convention (gaussian.py:122-123): rows M = b*l*ncb, row r = (token)*ncb + j holds
  * channels {k*ncb + j : k < g} of its token.
@@ -35,7 +40,7 @@
 extern "C" {
 #endif
 
-#define GQ_B200_ABI_VERSION 1
+#define GQ_B200_ABI_VERSION 2
 
 typedef void *gq_stream_t; /* cudaStream_t */
 
@@ -112,6 +117,26 @@ int gq_quantize_latent(const gq_codebook_t *cb, const float *z, const float *eps
  * err_flag (may be NULL): device int32 set to 1 if any index is outside [0,N). */
 int gq_dequant(const gq_codebook_t *cb, const int64_t *idx, float *out, int64_t b, int64_t l,
                int ncb, int layout, int32_t *err_flag, gq_stream_t stream);
+
+/* ---- packed index stream (opt-in; int64 stays the default wire format) -----------------------
+ * Width in bytes: gq_index_width(N) = 2 when N <= 65536, else 4 (N < 2^31).  packed: n elements of
+ * that width, same element order as idx.  err_flag (may be NULL): set to 1 if an index is outside
+ * [0,N) (it is then stored truncated).  gq_dequant_packed == gq_dequant on the unpacked indices. */
+int gq_index_width(int64_t N);
+int gq_pack_indices(const int64_t *idx, int64_t n, int64_t N, void *packed, int32_t *err_flag,
+                    gq_stream_t stream);
+int gq_unpack_indices(const void *packed, int64_t n, int64_t N, int64_t *idx, gq_stream_t stream);
+int gq_dequant_packed(const gq_codebook_t *cb, const void *packed, float *out, int64_t b, int64_t l,
+                      int ncb, int layout, int32_t *err_flag, gq_stream_t stream);
+
+/* ---- codebook usage ------------------------------------------------------------------------
+ * gq_index_histogram: hist[idx[i]] += 1 for i < n (hist: device uint64[N], ACCUMULATED -- zero it
+ * once, call per batch, like the reference's all_hist); out-of-range indices are skipped and
+ * flagged.  gq_usage_entropy: out = device float[2] = {usage, entropy_bits} with
+ * usage = 1 - (#empty bins)/N, p = hist/sum(hist), entropy = -sum p*log2(p + 1e-5), fp32. */
+int gq_index_histogram(const int64_t *idx, int64_t n, int64_t N, uint64_t *hist, int32_t *err_flag,
+                       gq_stream_t stream);
+int gq_usage_entropy(const uint64_t *hist, int64_t N, float *out, gq_stream_t stream);
 
 /* ---- train-branch KL penalty ------------------------------------------------------------
  * z: fp32 [b,l,2C] or [b,2C,h,w]; eps: fp32 noise shaped like mu (torch.randn_like, kept on

@@ -148,3 +148,43 @@ def kl(z_blc, group: int, n_samples_log2: int, tolerance: float = 0.5, lam: floa
         "bits_max": stats[2],
         "kl2": kl2,
     }
+
+
+# ---- index stream after the quantizer (numpy restatements; test infrastructure like the rest) ----------
+def index_histogram(idx, n_samples, hist=None):
+    """eval.py:127,152-154: all_hist (zeros(N)) += torch.histogram(indices.float(), torch.range(0, N))[0].
+    Bin i counts the indices equal to i; values outside [0, N) are dropped.  int64 counts."""
+    import numpy as _np
+    idx = _np.asarray(idx).reshape(-1)
+    ok = (idx >= 0) & (idx < n_samples)
+    h = _np.bincount(idx[ok].astype(_np.int64), minlength=int(n_samples)).astype(_np.int64)
+    if hist is None:
+        return h
+    hist += h
+    return hist
+
+
+def usage_entropy(hist):
+    """cal_ent, eval.py:137-141, in the reference's fp32 tensor arithmetic:
+    usage = 1 - sum(hist == 0)/N; p = hist / sum(hist); ent = -sum(p * log2(p + 1e-5))."""
+    import numpy as _np
+    h = _np.asarray(hist).astype(_np.float32)
+    unused = _np.float32((h == 0).astype(_np.float32).sum(dtype=_np.float32)) / _np.float32(h.shape[0])
+    p = h / h.sum(dtype=_np.float32)
+    ent = -(p * _np.log2(p + _np.float32(1e-5))).sum(dtype=_np.float32)
+    return float(_np.float32(1) - unused), float(ent)
+
+
+def packed_dtype(n_samples):
+    import numpy as _np
+    return _np.uint16 if n_samples <= 65536 else _np.uint32
+
+
+def pack_indices(idx, n_samples):
+    import numpy as _np
+    return _np.asarray(idx).astype(packed_dtype(n_samples))
+
+
+def unpack_indices(packed):
+    import numpy as _np
+    return _np.asarray(packed).astype(_np.int64)

@@ -7,7 +7,7 @@ SRC="vq-vae-from-gaussian-vae_b200/csrc"
 i=0
 for flags in "$@"; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 $flags -Xcompiler -fPIC -shared \
-    -o scripts/_build/libgq_v$i.so $SRC/gq_api.cu $SRC/gq_kernels.cu $SRC/gq_kl.cu $SRC/gq_tc.cu &
+    -o scripts/_build/libgq_v$i.so $SRC/gq_api.cu $SRC/gq_kernels.cu $SRC/gq_kl.cu $SRC/gq_tc.cu $SRC/gq_tokens.cu &
   i=$((i+1))
 done
 wait

@@ -106,6 +106,15 @@ def main():
         ms = timed(lambda: check(L.gq_dequant(cb.handle, _ptr(idx), _ptr(o16), bb, ll, 1, layout, None, _stream()), "dq"),
                    flush=flush)
         rec(name, ms, idx.numel() * 8 + idx.numel() * 16 * 4)
+    # --- index stream: histogram (8 B read per index), pack / unpack (8 B + 2 B per index), 16 M indices
+    n_idx = 1 << 24
+    big = torch.randint(0, 65536, (n_idx,), device=dev)
+    hist = torch.zeros(65536, dtype=torch.int64, device=dev)
+    rec("index_histogram", timed(lambda: gq_b200.index_histogram(big, 65536, hist), iters=20, flush=flush), n_idx * 8)
+    rec("pack_indices_u16", timed(lambda: gq_b200.pack_indices(big, 65536), iters=20, flush=flush), n_idx * 10)
+    pk = gq_b200.pack_indices(big, 65536)
+    rec("unpack_indices_u16", timed(lambda: gq_b200.unpack_indices(pk, 65536), iters=20, flush=flush), n_idx * 10)
+    del big, pk
     # --- legacy score matrix: M=8192 rows x 65536 (2.1 GB fp32 out, write-bound)
     M = 8192
     mu = torch.randn(M, 16, device=dev)

@@ -19,7 +19,7 @@ OUT = os.path.join(ROOT, "scripts", "_build", "libgq_b200_prof.so")
 
 def build():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    src = [os.path.join(PKG, "csrc", f) for f in ("gq_api.cu", "gq_kernels.cu", "gq_kl.cu", "gq_tc.cu")]
+    src = [os.path.join(PKG, "csrc", f) for f in ("gq_api.cu", "gq_kernels.cu", "gq_kl.cu", "gq_tc.cu", "gq_tokens.cu")]
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-DGQ_TC_TRACE",
            "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + src + sys.argv[2:]
     subprocess.check_call(cmd)

@@ -170,8 +170,38 @@ def legacy_case(name, M, N, dim, beta, seed=0):
     print(name, "ok")
 
 
+def usage_case(name, N, n, seed=0, batches=3):
+    """Codebook usage / entropy exactly as eval.py computes them: all_hist = zeros(N) (eval.py:127);
+    per batch `hist = torch.histogram(indices.cpu().float(), torch.range(0, N)); all_hist += hist[0]`
+    (eval.py:152-154); then cal_ent (eval.py:137-141): usage = 1 - mean(hist == 0), p = hist / sum(hist),
+    ent = -sum(p * log2(p + 1e-5)).  The index batches are synthetic (skewed, with unused codewords)."""
+    import warnings
+    gen = torch.Generator().manual_seed(seed)
+    all_hist = torch.zeros([N])
+    out = {"N": N}
+    for bi in range(batches):
+        # squared uniform -> heavy on low indices, and a block of codewords that is never used
+        u = torch.rand(n, generator=gen)
+        idx = (u * u * (N - N // 7)).long().clamp_(0, N - 1)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            hist = torch.histogram(idx.float(), torch.range(0, N))
+        all_hist += hist[0]
+        out[f"idx{bi}"] = idx.numpy()
+    usage = torch.sum((all_hist == 0).to(dtype=torch.float32)) / all_hist.shape[0]
+    p = all_hist / torch.sum(all_hist)
+    ent = -torch.sum(p * torch.log2(p + 1e-5))
+    out.update(batches=batches, hist=all_hist.numpy(), usage=float(1 - usage), entropy=float(ent))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok", float(1 - usage), float(ent))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "usage":   # only the codebook-usage fixtures
+        usage_case("usage_n65536", 65536, 60000)
+        usage_case("usage_n1000", 1000, 5000, seed=1, batches=2)
+        sys.exit(0)
     eval_case("eval_bchw_g16_n1024", "bchw", 1, (8, 8), 16, 16, 1024, "trained")
     eval_case("eval_blc_g16_n4096", "blc", 2, 32, 16, 16, 4096, "trained", seed=1)
     eval_case("eval_bchw_g4_n4096", "bchw", 2, (4, 4), 16, 4, 4096, "trained", seed=2)
@@ -188,3 +218,5 @@ if __name__ == "__main__":
     gq2_case("gq2_blc_dim8", (2, 16, 32), 8, 1024, 2, seed=1)
     legacy_case("legacy_b1", 24, 512, 16, 1.0)
     legacy_case("legacy_b07", 16, 256, 8, 0.7, seed=1)
+    usage_case("usage_n65536", 65536, 60000)
+    usage_case("usage_n1000", 1000, 5000, seed=1, batches=2)

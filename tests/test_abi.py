@@ -27,7 +27,8 @@ def test_header_declares_expected_surface():
     names = declared_functions()
     for must in ["gq_scores_f32", "gq_codebook_create", "gq_codebook_destroy", "gq_quantize", "gq_quantize_exact",
                  "gq_quantize_workspace_bytes", "gq_dequant", "gq_kl_fwd", "gq_kl_bwd", "gq_kl_workspace_bytes",
-                 "gq_abi_version", "gq_last_error", "gq_launch_count"]:
+                 "gq_abi_version", "gq_last_error", "gq_launch_count", "gq_index_width", "gq_pack_indices",
+                 "gq_unpack_indices", "gq_dequant_packed", "gq_index_histogram", "gq_usage_entropy"]:
         assert must in names
 
 
@@ -111,3 +112,29 @@ def test_streamk_plan_covers_every_step_once(lib, N, M, sms):
         assert segs == list(range(len(segs)))
         first, last = (u * tiles) // spc, (u * tiles + tiles - 1) // spc
         assert len(segs) == last - first + 1
+
+
+def test_index_stream_entry_points_validate_without_gpu(lib):
+    lib.gq_last_error.restype = ctypes.c_char_p
+    w = lib.gq_index_width
+    w.restype, w.argtypes = ctypes.c_int, [ctypes.c_int64]
+    assert [w(n) for n in (1, 4096, 65536, 65537, 1 << 18)] == [2, 2, 2, 4, 4]
+    pk = lib.gq_pack_indices
+    pk.restype, pk.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    assert pk(None, 0, 65536, None, None, None) == 0            # empty stream is a no-op
+    assert pk(None, 8, 65536, None, None, None) == -1           # null pointers
+    assert pk(None, 8, 0, None, None, None) == -1               # no codebook
+    assert pk(None, 8, 1 << 31, None, None, None) == -1         # does not fit 32 bits
+    up = lib.gq_unpack_indices
+    up.restype, up.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    assert up(None, 0, 65536, None, None) == 0 and up(None, 3, 65536, None, None) == -1
+    h = lib.gq_index_histogram
+    h.restype, h.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    assert h(None, 4, 16, None, None, None) == -1 and b"hist is null" in lib.gq_last_error()
+    u = lib.gq_usage_entropy
+    u.restype, u.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    assert u(None, 16, None, None) == -1
+    d = lib.gq_dequant_packed
+    d.restype = ctypes.c_int
+    d.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    assert d(None, None, None, 1, 1, 1, 0, None, None) == -1 and b"handle is null" in lib.gq_last_error()

@@ -49,12 +49,15 @@ def _worker(rank, world, port, batch, out_dir):
     w = np.where(kl2 > 10.5, 2.0, np.where(kl2 < 9.5, 0.7, 1.0))
     stats = torch.tensor([0, 0, r["bits_min"], r["bits_max"], kl2.sum(), (w * kl2).sum(), 0, 0], dtype=torch.float32)
     glob = gd.global_kl_stats(stats, kl2.size, batch, 1.3)
+    # codebook-usage histogram of the local shard, summed over ranks
+    hist = gd.global_usage_histogram(torch.from_numpy(oracle.index_histogram(idx, 1024)))
     if rank == 0:
         mu_a, lv_a = z[..., :C].reshape(-1, g), z[..., C:].reshape(-1, g)
         std_a = torch.exp(0.5 * lv_a)
         want, _, _, _ = oracle.quantize(mu_a.numpy(), std_a.numpy(), std_a.log().numpy(), cb, nlp)
         ra = oracle.kl(z.numpy(), g, 10, 0.5, 1.3, 0.7, 2.0)
         np.savez(os.path.join(out_dir, "r0.npz"), full=full.numpy(), want=want.reshape(batch, l, 1), glob=glob.numpy(),
+                 hist=hist.numpy(), hist_want=oracle.index_histogram(want, 1024),
                  ref=np.array([ra["kl_loss"], ra["bits_mean"], ra["bits_min"], ra["bits_max"]]))
     dist.barrier()
     dist.destroy_process_group()
@@ -67,6 +70,7 @@ def test_sharded_rows_match_single_process(tmp_path, batch):
     r = np.load(tmp_path / "r0.npz")
     assert np.array_equal(r["full"], r["want"])
     np.testing.assert_allclose(r["glob"], r["ref"], rtol=1e-5)
+    assert np.array_equal(r["hist"], r["hist_want"]) and r["hist"].sum() == batch * 16
 
 
 def test_shard_bounds_partition():

@@ -497,3 +497,91 @@ def test_quantize_degenerate_rows(gq):
     std_t = np.full((4, g), 0.3, np.float32)
     it, _ = gq.quantize_rows(h2, dev(mu_t), dev(std_t), dev(np.log(std_t)))
     assert (it.cpu().numpy() == 5).all()
+
+
+# ---- index stream after the quantizer: integer work, bit-exact ----------------------
+@pytest.mark.parametrize("name", ["usage_n65536", "usage_n1000"])
+def test_usage_histogram_and_entropy_golden(gq, name):
+    """gq_index_histogram accumulates exactly torch.histogram's counts (eval.py:152-154);
+    gq_usage_entropy = cal_ent (eval.py:137-141) within fp32 reduction-order tolerance 1e-5."""
+    g = load_golden(name)
+    N = int(g["N"])
+    hist = None
+    for bi in range(int(g["batches"])):
+        hist = gq.index_histogram(dev(g[f"idx{bi}"]), N, hist)
+    assert np.array_equal(hist.cpu().numpy(), g["hist"].astype(np.int64))
+    usage, ent = gq.usage_entropy(hist)
+    assert float(usage) == pytest.approx(float(g["usage"]), rel=1e-6)
+    assert float(ent) == pytest.approx(float(g["entropy"]), rel=1e-5)
+    # and against the oracle on the same histogram
+    o_usage, o_ent = oracle.usage_entropy(hist.cpu().numpy())
+    assert float(usage) == pytest.approx(o_usage, rel=1e-6) and float(ent) == pytest.approx(o_ent, rel=1e-5)
+
+
+@pytest.mark.parametrize("n,N", [(0, 100), (1, 100), (7, 65536), (4099, 65536), (1 << 20, 65536), (100003, 1 << 18)])
+def test_histogram_sizes_alignment_and_range(gq, n, N):
+    rng = np.random.RandomState(n % 1000 + 3)
+    idx = rng.randint(0, N, size=n + 1).astype(np.int64)
+    t = dev(idx)
+    for view in (t[:n], t[1:]):            # 16-byte aligned and 8-byte-offset pointers
+        h = gq.index_histogram(view, N)
+        assert np.array_equal(h.cpu().numpy(), oracle.index_histogram(view.cpu().numpy(), N))
+    if n:
+        bad = t[:n].clone()
+        bad[n // 2] = N
+        with pytest.raises(IndexError):
+            gq.index_histogram(bad, N, check_range=True)
+        h = gq.index_histogram(bad, N)      # unchecked: the stray index is dropped like torch.histogram does
+        assert int(h.sum()) == n - 1
+
+
+@pytest.mark.parametrize("n,N", [(0, 100), (5, 1000), (8, 65536), (4099, 65536), (1 << 18, 65536), (777, 65537), (100003, 1 << 18)])
+def test_pack_unpack_roundtrip(gq, n, N):
+    rng = np.random.RandomState(n % 1000 + 11)
+    idx = rng.randint(0, N, size=n + 1).astype(np.int64)
+    if n > 2:
+        idx[0], idx[1] = 0, N - 1           # extremes survive
+    t = dev(idx)
+    for view in (t[:n], t[1:]):
+        p = gq.pack_indices(view, N, check_range=True)
+        assert p.dtype == (torch.uint16 if N <= 65536 else torch.int32) and p.shape == view.shape
+        assert np.array_equal(p.cpu().numpy().astype(np.int64), oracle.pack_indices(view.cpu().numpy(), N).astype(np.int64))
+        assert torch.equal(gq.unpack_indices(p, N), view)
+    if n:
+        bad = t[:n].clone()
+        bad[-1] = -1
+        with pytest.raises(IndexError):
+            gq.pack_indices(bad, N, check_range=True)
+
+
+@pytest.mark.parametrize("fmt,g,N", [("bchw", 16, 65536), ("blc", 16, 65536), ("bchw", 4, 4096), ("blc", 8, 70000)])
+def test_dequant_reads_packed_stream(gq, fmt, g, N):
+    """dequant(pack(indices)) == dequant(indices) bit for bit (gaussian.py:162-178), uint16 and int32 streams."""
+    cb, nlp, h = big_codebook(gq, N, g)
+    ncb = 16 // g
+    gen = torch.Generator().manual_seed(N % 1000 + g)
+    shape = (3, ncb, 6, 5) if fmt == "bchw" else (3, 30, ncb)
+    idx = torch.randint(0, N, shape, generator=gen).cuda()
+    layout = gq.ops.GQ_LAYOUT_BCHW if fmt == "bchw" else gq.ops.GQ_LAYOUT_BLC
+    want = gq.dequant(h, idx, layout)
+    packed = gq.pack_indices(idx, N)
+    assert packed.element_size() == (2 if N <= 65536 else 4)
+    assert torch.equal(gq.dequant(h, packed, layout), want)
+    if N <= 65536:
+        with pytest.raises(RuntimeError):
+            gq.dequant(h, idx.int(), layout)       # wrong width for this codebook
+
+
+def test_module_index_stream_helpers(gq):
+    reg = gq.GaussianQuantRegularizer(format="bchw", n_samples=4096, group=16, backend="cuda").cuda().eval()
+    z = torch.randn(2, 32, 8, 8, device="cuda") * 0.5
+    zhat, info = reg(z)
+    packed = reg.pack_indices(info["indices"])
+    assert packed.dtype == torch.uint16
+    assert torch.equal(reg.dequant(packed), zhat) and torch.equal(reg.unpack_indices(packed), info["indices"])
+    hist = reg.accumulate_usage(info["indices"])
+    hist = reg.accumulate_usage(info["indices"], hist)
+    assert int(hist.sum()) == 2 * info["indices"].numel()
+    usage, ent = reg.codebook_usage(hist)
+    o_usage, o_ent = oracle.usage_entropy(hist.cpu().numpy())
+    assert float(usage) == pytest.approx(o_usage, rel=1e-6) and float(ent) == pytest.approx(o_ent, rel=1e-5)

@@ -100,3 +100,29 @@ def test_empty_rows():
     e = np.zeros((0, 8), np.float32)
     idx, zhat, _, _ = oracle.quantize(e, e, e, cb, nlp)
     assert idx.shape == (0,) and zhat.shape == (0, 8)
+
+
+# ---- index stream after the quantizer -------------------------------------------
+@pytest.mark.parametrize("name", ["usage_n65536", "usage_n1000"])
+def test_usage_histogram_and_entropy_match_reference(name):
+    """oracle.index_histogram / usage_entropy against fixtures produced with the reference's own
+    torch calls (eval.py:127,137-141,152-154; tests/golden/make_golden.py usage_case)."""
+    g = load_golden(name)
+    N = int(g["N"])
+    hist = None
+    for bi in range(int(g["batches"])):
+        hist = oracle.index_histogram(g[f"idx{bi}"], N, hist)
+    assert np.array_equal(hist, g["hist"].astype(np.int64))
+    usage, ent = oracle.usage_entropy(hist)
+    assert usage == pytest.approx(float(g["usage"]), rel=1e-6)
+    assert ent == pytest.approx(float(g["entropy"]), rel=1e-5)
+
+
+def test_histogram_drops_out_of_range_and_pack_roundtrip():
+    idx = np.array([0, 5, 5, 9, -1, 10, 3], dtype=np.int64)
+    assert oracle.index_histogram(idx, 10).tolist() == [1, 0, 0, 1, 0, 2, 0, 0, 0, 1]
+    for N in (10, 65536, 65537, 1 << 18):
+        v = np.random.RandomState(N % 97).randint(0, N, size=1001).astype(np.int64)
+        p = oracle.pack_indices(v, N)
+        assert p.dtype == (np.uint16 if N <= 65536 else np.uint32)
+        assert np.array_equal(oracle.unpack_indices(p), v)

@@ -16,7 +16,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent / "gq_b200"
 CSRC = PKG_DIR.parent / "csrc"
 LIB = PKG_DIR / "libgq_b200.so"
-SOURCES = ["gq_api.cu", "gq_kernels.cu", "gq_kl.cu", "gq_tc.cu"]
+SOURCES = ["gq_api.cu", "gq_kernels.cu", "gq_kl.cu", "gq_tc.cu", "gq_tokens.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

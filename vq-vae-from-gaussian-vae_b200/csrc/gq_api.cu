@@ -201,7 +201,52 @@ int gq_dequant(const gq_codebook_t *cb, const int64_t *idx, float *out, int64_t 
     if (layout != GQ_LAYOUT_BLC && layout != GQ_LAYOUT_BCHW) { set_error("gq_dequant: bad layout %d", layout); return GQ_ERR_INVALID; }
     if (b * l == 0) return GQ_OK;
     if (!idx || !out) { set_error("gq_dequant: null pointer"); return GQ_ERR_INVALID; }
-    return launch_dequant(cb, idx, out, b, l, ncb, layout, err_flag, (cudaStream_t)stream);
+    return launch_dequant(cb, idx, 8, out, b, l, ncb, layout, err_flag, (cudaStream_t)stream);
+}
+
+int gq_index_width(int64_t N) { return index_width(N); }
+
+int gq_dequant_packed(const gq_codebook_t *cb, const void *packed, float *out, int64_t b, int64_t l, int ncb,
+                      int layout, int32_t *err_flag, gq_stream_t stream)
+{
+    if (!cb) { set_error("gq_dequant_packed: codebook handle is null"); return GQ_ERR_INVALID; }
+    if (b < 0 || l < 0 || ncb <= 0) { set_error("gq_dequant_packed: bad sizes"); return GQ_ERR_INVALID; }
+    if (layout != GQ_LAYOUT_BLC && layout != GQ_LAYOUT_BCHW) { set_error("gq_dequant_packed: bad layout %d", layout); return GQ_ERR_INVALID; }
+    if (b * l == 0) return GQ_OK;
+    if (!packed || !out) { set_error("gq_dequant_packed: null pointer"); return GQ_ERR_INVALID; }
+    return launch_dequant(cb, packed, index_width(cb->N), out, b, l, ncb, layout, err_flag, (cudaStream_t)stream);
+}
+
+int gq_pack_indices(const int64_t *idx, int64_t n, int64_t N, void *packed, int32_t *err_flag, gq_stream_t stream)
+{
+    if (n < 0 || N <= 0 || N > 0x7fffffffll) { set_error("gq_pack_indices: bad sizes n=%lld N=%lld", (long long)n, (long long)N); return GQ_ERR_INVALID; }
+    if (n == 0) return GQ_OK;
+    if (!idx || !packed) { set_error("gq_pack_indices: null pointer"); return GQ_ERR_INVALID; }
+    return launch_pack_indices(idx, n, N, packed, err_flag, (cudaStream_t)stream);
+}
+
+int gq_unpack_indices(const void *packed, int64_t n, int64_t N, int64_t *idx, gq_stream_t stream)
+{
+    if (n < 0 || N <= 0 || N > 0x7fffffffll) { set_error("gq_unpack_indices: bad sizes n=%lld N=%lld", (long long)n, (long long)N); return GQ_ERR_INVALID; }
+    if (n == 0) return GQ_OK;
+    if (!idx || !packed) { set_error("gq_unpack_indices: null pointer"); return GQ_ERR_INVALID; }
+    return launch_unpack_indices(packed, n, N, idx, (cudaStream_t)stream);
+}
+
+int gq_index_histogram(const int64_t *idx, int64_t n, int64_t N, uint64_t *hist, int32_t *err_flag, gq_stream_t stream)
+{
+    if (n < 0 || N <= 0) { set_error("gq_index_histogram: bad sizes n=%lld N=%lld", (long long)n, (long long)N); return GQ_ERR_INVALID; }
+    if (!hist) { set_error("gq_index_histogram: hist is null"); return GQ_ERR_INVALID; }
+    if (n == 0) return GQ_OK;
+    if (!idx) { set_error("gq_index_histogram: idx is null"); return GQ_ERR_INVALID; }
+    return launch_index_histogram(idx, n, N, reinterpret_cast<unsigned long long *>(hist), err_flag, (cudaStream_t)stream);
+}
+
+int gq_usage_entropy(const uint64_t *hist, int64_t N, float *out, gq_stream_t stream)
+{
+    if (N <= 0) { set_error("gq_usage_entropy: bad size N=%lld", (long long)N); return GQ_ERR_INVALID; }
+    if (!hist || !out) { set_error("gq_usage_entropy: null pointer"); return GQ_ERR_INVALID; }
+    return launch_usage_entropy(reinterpret_cast<const unsigned long long *>(hist), N, out, (cudaStream_t)stream);
 }
 
 int64_t gq_kl_workspace_bytes(int64_t b, int64_t l, int C) { return kl_workspace_bytes(b, l, C); }

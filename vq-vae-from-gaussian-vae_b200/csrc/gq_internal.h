@@ -21,8 +21,16 @@ int launch_exact_sliced(const gq_codebook *cb, const float *mu, const float *std
 
 int launch_codebook_prep(gq_codebook *cb, const float *nlp_in, cudaStream_t stream);
 
-int launch_dequant(const gq_codebook *cb, const int64_t *idx, float *out, int64_t b, int64_t l,
+int launch_dequant(const gq_codebook *cb, const void *idx, int idx_bytes, float *out, int64_t b, int64_t l,
                    int ncb, int layout, int32_t *err_flag, cudaStream_t stream);
+
+// index stream utilities (gq_tokens.cu)
+int launch_index_histogram(const int64_t *idx, int64_t n, int64_t N, unsigned long long *hist, int32_t *err_flag,
+                           cudaStream_t stream);
+int launch_usage_entropy(const unsigned long long *hist, int64_t N, float *out, cudaStream_t stream);
+int index_width(int64_t N);
+int launch_pack_indices(const int64_t *idx, int64_t n, int64_t N, void *packed, int32_t *err_flag, cudaStream_t stream);
+int launch_unpack_indices(const void *packed, int64_t n, int64_t N, int64_t *idx, cudaStream_t stream);
 
 // tensor-core search (gq_tc.cu)
 int64_t tc_workspace_bytes(const gq_codebook *cb, int64_t M);

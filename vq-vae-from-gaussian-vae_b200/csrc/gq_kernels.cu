@@ -433,9 +433,9 @@ int launch_codebook_prep(gq_codebook *cb, const float *nlp_in, cudaStream_t stre
 // In BCHW consecutive threads take consecutive tokens, so both the index reads and the g
 // strided stores are coalesced; in BLC with ncb == 1 the row is stored as float4s.
 // ------------------------------------------------------------------------------------------
-template <int G>
+template <int G, typename IdxT>
 __global__ void __launch_bounds__(256)
-dequant_kernel(const int64_t *__restrict__ idx, const float *__restrict__ cb, float *__restrict__ out,
+dequant_kernel(const IdxT *__restrict__ idx, const float *__restrict__ cb, float *__restrict__ out,
                int64_t b, int64_t l, int ncb, int64_t N, int layout, int32_t *err_flag)
 {
     const int64_t total = b * l * ncb;
@@ -451,7 +451,7 @@ dequant_kernel(const int64_t *__restrict__ idx, const float *__restrict__ cb, fl
         // G/4 lanes per row, one 16-byte quarter each: loads and stores are both lane-contiguous
         constexpr int Q = (G >= 4) ? G / 4 : 1;
         for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total * Q; e += (int64_t)gridDim.x * blockDim.x) {
-            int64_t id = __ldg(idx + e / Q);
+            int64_t id = (int64_t)__ldg(idx + e / Q);
             if (id < 0 || id >= N) {
                 if (err_flag) *err_flag = 1;
                 id = 0;
@@ -473,7 +473,7 @@ dequant_kernel(const int64_t *__restrict__ idx, const float *__restrict__ cb, fl
             t = (i / ncb) % l;
             bi = i / (l * ncb);
         }
-        int64_t id = idx[i];
+        int64_t id = (int64_t)idx[i];
         if (id < 0 || id >= N) {
             if (err_flag) *err_flag = 1;
             id = 0;
@@ -498,15 +498,16 @@ dequant_kernel(const int64_t *__restrict__ idx, const float *__restrict__ cb, fl
     }
 }
 
-int launch_dequant(const gq_codebook *cb, const int64_t *idx, float *out, int64_t b, int64_t l, int ncb,
-                   int layout, int32_t *err_flag, cudaStream_t stream)
+template <typename IdxT>
+static int launch_dequant_t(const gq_codebook *cb, const IdxT *idx, float *out, int64_t b, int64_t l, int ncb,
+                            int layout, int32_t *err_flag, cudaStream_t stream)
 {
     const int64_t total = b * l * ncb;
     if (total == 0) return GQ_OK;
     int64_t items = total;
     if (layout == GQ_LAYOUT_BLC && ncb == 1 && cb->g % 4 == 0) items = total * (cb->g / 4);
     int blocks = (int)imin((items + 255) / 256, 148 * 16);
-#define GQ_DQ(GG) dequant_kernel<GG><<<blocks, 256, 0, stream>>>(idx, cb->cb, out, b, l, ncb, cb->N, layout, err_flag)
+#define GQ_DQ(GG) dequant_kernel<GG, IdxT><<<blocks, 256, 0, stream>>>(idx, cb->cb, out, b, l, ncb, cb->N, layout, err_flag)
     switch (cb->g) {
     case 1: GQ_DQ(1); break;
     case 2: GQ_DQ(2); break;
@@ -519,6 +520,18 @@ int launch_dequant(const gq_codebook *cb, const int64_t *idx, float *out, int64_
 #undef GQ_DQ
     count_launch();
     return check_launch("dequant_kernel");
+}
+
+// idx_bytes: 8 = int64 (the reference's wire format), 4 / 2 = packed stream (gq_tokens.cu)
+int launch_dequant(const gq_codebook *cb, const void *idx, int idx_bytes, float *out, int64_t b, int64_t l, int ncb,
+                   int layout, int32_t *err_flag, cudaStream_t stream)
+{
+    switch (idx_bytes) {
+    case 8: return launch_dequant_t(cb, static_cast<const int64_t *>(idx), out, b, l, ncb, layout, err_flag, stream);
+    case 4: return launch_dequant_t(cb, static_cast<const uint32_t *>(idx), out, b, l, ncb, layout, err_flag, stream);
+    case 2: return launch_dequant_t(cb, static_cast<const uint16_t *>(idx), out, b, l, ncb, layout, err_flag, stream);
+    default: set_error("index width %d unsupported", idx_bytes); return GQ_ERR_INVALID;
+    }
 }
 
 }  // namespace gq

@@ -10,11 +10,12 @@ from . import _lib
 _lib.lib()  # fail loudly at import time if the CUDA library is absent or stale
 
 from . import ops  # noqa: E402
-from .ops import (Codebook, dequant, kl_penalty, launch_count, quantize_latent, quantize_rows,  # noqa: E402
-                  scores_legacy_)
+from .ops import (Codebook, dequant, index_histogram, kl_penalty, launch_count, pack_indices,  # noqa: E402
+                  packed_dtype, quantize_latent, quantize_rows, scores_legacy_, unpack_indices, usage_entropy)
 from .regularizer import GaussianQuantRegularizer, GaussianQuantRegularizer2, prior_samples  # noqa: E402
 
 __all__ = [
     "ops", "Codebook", "quantize_rows", "quantize_latent", "dequant", "kl_penalty", "scores_legacy_", "launch_count",
+    "pack_indices", "unpack_indices", "packed_dtype", "index_histogram", "usage_entropy",
     "GaussianQuantRegularizer", "GaussianQuantRegularizer2", "prior_samples",
 ]

@@ -18,7 +18,7 @@ LIB_PATH = Path(os.environ.get("GQ_B200_LIB") or (Path(__file__).resolve().paren
 GQ_OK = 0
 GQ_LAYOUT_BLC = 0
 GQ_LAYOUT_BCHW = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/gq_b200.h one to one
 PROTOTYPES = {
@@ -43,6 +43,13 @@ PROTOTYPES = {
                                   c_void_p, c_void_p]),
     "gq_dequant": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
                            c_void_p]),
+    "gq_index_width": (c_int, [c_int64]),
+    "gq_pack_indices": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "gq_unpack_indices": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "gq_dequant_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
+                                  c_void_p]),
+    "gq_index_histogram": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "gq_usage_entropy": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gq_kl_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),
     "gq_kl_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                           c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, c_float,

@@ -76,3 +76,13 @@ def global_kl_stats(stats: torch.Tensor, local_groups: int, global_batch: int, l
     out[2] = mn
     out[3] = mx
     return out
+
+
+def global_usage_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum rank-local codebook-usage histograms (int64 [n_samples], gq_index_histogram) over all ranks,
+    in place: the one exchange a sharded evaluation needs before cal_ent (eval.py:137-141).  Integer
+    SUM, so the result is independent of the reduction order."""
+    if hist.dtype != torch.int64:
+        raise RuntimeError("hist must be int64")
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist

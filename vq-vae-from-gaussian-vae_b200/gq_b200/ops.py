@@ -207,8 +207,11 @@ def quantize_latent(cb: Codebook, z: torch.Tensor, layout: int, eps: Optional[to
 
 def dequant(cb: Codebook, indices: torch.Tensor, layout: int, check_range: bool = False) -> torch.Tensor:
     """gaussian.py:162-178.  indices int64 [b,l,ncb] (BLC) or [b,ncb,h,w] (BCHW)."""
-    if indices.dtype != torch.int64:
-        raise RuntimeError(f"indices must be int64, got {indices.dtype}")
+    packed = indices.dtype in (torch.uint16, torch.int32)
+    if indices.dtype != torch.int64 and not packed:
+        raise RuntimeError(f"indices must be int64 (or a packed uint16/int32 stream), got {indices.dtype}")
+    if packed and indices.dtype != packed_dtype(cb.N):
+        raise RuntimeError(f"a {cb.N}-entry codebook packs to {packed_dtype(cb.N)}, got {indices.dtype}")
     if not indices.is_cuda:
         raise NotImplementedError("indices must be a CUDA tensor (no CPU implementation exists)")
     indices = indices.contiguous()
@@ -225,11 +228,82 @@ def dequant(cb: Codebook, indices: torch.Tensor, layout: int, check_range: bool 
         out = torch.empty(b, l, ncb * cb.g, dtype=torch.float32, device=indices.device)
     flag = torch.zeros(1, dtype=torch.int32, device=indices.device) if check_range else None
     with torch.cuda.device(indices.device):
-        check(_lib.lib().gq_dequant(cb.handle, _ptr(indices), _ptr(out), b, l, ncb, layout, _ptr(flag),
-                                    _stream()), "gq_dequant")
+        fn = _lib.lib().gq_dequant_packed if packed else _lib.lib().gq_dequant
+        check(fn(cb.handle, _ptr(indices), _ptr(out), b, l, ncb, layout, _ptr(flag), _stream()), "gq_dequant")
     if check_range and int(flag.item()):
         raise IndexError("index out of range in dequant")  # torch.index_select raises likewise
     return out
+
+
+# ---- index stream utilities ----------------------------------------------------
+def packed_dtype(n_samples: int) -> torch.dtype:
+    """dtype of the packed index stream of an n_samples-entry codebook (gq_index_width)."""
+    return torch.uint16 if int(_lib.lib().gq_index_width(int(n_samples))) == 2 else torch.int32
+
+
+def _require_cuda_idx(indices: torch.Tensor) -> torch.Tensor:
+    if indices.dtype != torch.int64:
+        raise RuntimeError(f"indices must be int64, got {indices.dtype}")
+    if not indices.is_cuda:
+        raise NotImplementedError("indices must be a CUDA tensor (no CPU implementation exists)")
+    return indices.contiguous()
+
+
+def pack_indices(indices: torch.Tensor, n_samples: int, check_range: bool = False) -> torch.Tensor:
+    """int64 indices (any shape) -> uint16 (n_samples <= 65536) / int32 stream of the same shape.
+    Opt-in wire format: the reference carries int64 everywhere (gaussian.py:138,159)."""
+    indices = _require_cuda_idx(indices)
+    out = torch.empty(indices.shape, dtype=packed_dtype(n_samples), device=indices.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=indices.device) if check_range else None
+    with torch.cuda.device(indices.device):
+        check(_lib.lib().gq_pack_indices(_ptr(indices), indices.numel(), int(n_samples), _ptr(out), _ptr(flag),
+                                         _stream()), "gq_pack_indices")
+    if check_range and int(flag.item()):
+        raise IndexError("index out of range in pack_indices")
+    return out
+
+
+def unpack_indices(packed: torch.Tensor, n_samples: int) -> torch.Tensor:
+    """Inverse of pack_indices: -> int64, same shape."""
+    if packed.dtype != packed_dtype(n_samples):
+        raise RuntimeError(f"a {n_samples}-entry codebook packs to {packed_dtype(n_samples)}, got {packed.dtype}")
+    if not packed.is_cuda:
+        raise NotImplementedError("packed indices must be a CUDA tensor (no CPU implementation exists)")
+    packed = packed.contiguous()
+    out = torch.empty(packed.shape, dtype=torch.int64, device=packed.device)
+    with torch.cuda.device(packed.device):
+        check(_lib.lib().gq_unpack_indices(_ptr(packed), packed.numel(), int(n_samples), _ptr(out), _stream()),
+              "gq_unpack_indices")
+    return out
+
+
+def index_histogram(indices: torch.Tensor, n_samples: int, hist: Optional[torch.Tensor] = None,
+                    check_range: bool = False) -> torch.Tensor:
+    """hist[i] += #(indices == i) (eval.py:127,152-154: all_hist += torch.histogram(indices, range(0, N))).
+    hist: int64 [n_samples] on the same device, accumulated in place (created zeroed when None)."""
+    indices = _require_cuda_idx(indices)
+    if hist is None:
+        hist = torch.zeros(int(n_samples), dtype=torch.int64, device=indices.device)
+    if hist.dtype != torch.int64 or hist.numel() != int(n_samples) or not hist.is_contiguous() or hist.device != indices.device:
+        raise RuntimeError("hist must be a contiguous int64 tensor of n_samples bins on the indices' device")
+    flag = torch.zeros(1, dtype=torch.int32, device=indices.device) if check_range else None
+    with torch.cuda.device(indices.device):
+        check(_lib.lib().gq_index_histogram(_ptr(indices), indices.numel(), int(n_samples), _ptr(hist), _ptr(flag),
+                                            _stream()), "gq_index_histogram")
+    if check_range and int(flag.item()):
+        raise IndexError("index out of range in index_histogram")
+    return hist
+
+
+def usage_entropy(hist: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """cal_ent (eval.py:137-141): (codebook usage in [0,1], entropy in bits) as 0-dim fp32 tensors."""
+    if hist.dtype != torch.int64 or not hist.is_cuda:
+        raise RuntimeError("hist must be the int64 CUDA tensor index_histogram accumulates")
+    hist = hist.contiguous()
+    out = torch.empty(2, dtype=torch.float32, device=hist.device)
+    with torch.cuda.device(hist.device):
+        check(_lib.lib().gq_usage_entropy(_ptr(hist), hist.numel(), _ptr(out), _stream()), "gq_usage_entropy")
+    return out[0], out[1]
 
 
 class _KlPenalty(torch.autograd.Function):

@@ -162,8 +162,26 @@ class GaussianQuantRegularizer(_GQBase):
         return self._forward_eval(z)
 
     def dequant(self, indices):
+        """gaussian.py:162-178.  Also accepts the packed stream of `pack_indices` (uint16 / int32)."""
         layout = GQ_LAYOUT_BCHW if self.format == "bchw" else GQ_LAYOUT_BLC
         return ops.dequant(self._codebook(), indices, layout, check_range=True)
+
+    # ---- not in the reference module: the index stream after the quantizer (SURVEY 8f ranks 3-4) ----
+    def pack_indices(self, indices):
+        """int64 indices -> uint16 (n_samples <= 65536) / int32, same shape; `dequant` reads either."""
+        return ops.pack_indices(indices, self.n_samples, check_range=True)
+
+    def unpack_indices(self, packed):
+        return ops.unpack_indices(packed, self.n_samples)
+
+    def accumulate_usage(self, indices, hist=None):
+        """all_hist += histogram(indices) over the codebook (eval.py:127,152-154); returns the int64 histogram."""
+        return ops.index_histogram(indices, self.n_samples, hist, check_range=True)
+
+    @staticmethod
+    def codebook_usage(hist):
+        """cal_ent (eval.py:137-141) -> (usage, entropy_bits) 0-dim tensors."""
+        return ops.usage_entropy(hist)
 
 
 class GaussianQuantRegularizer2(_GQBase):
