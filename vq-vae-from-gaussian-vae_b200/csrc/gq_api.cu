@@ -103,7 +103,7 @@ int gq_codebook_create(const float *codebook, const float *nlp, int64_t N, int g
     gq_codebook *cb = new gq_codebook();
     cb->N = N;
     cb->g = g;
-    cb->kpad = (int)align_up(2 * g, 16);
+    cb->kpad = gq_image_kpad(g);
     cb->n_pad = align_up(N, 128);
     cb->beta = beta;
     cudaGetDevice(&cb->device);

@@ -95,11 +95,20 @@ __device__ __forceinline__ void load_row(const float *__restrict__ p, float (&v)
 
 }  // namespace gq
 
+// Operand-image geometry of the tensor-core search.  Groups g <= 4 use a split-precision image: with
+// K = 2g <= 8 the plain fp16 image leaves most of a K = 16 slice empty, and a 4-dimensional codebook of
+// 65 536 points is so dense that hundreds of codewords fall inside the fp16 error window of the best
+// one.  Three fp16 products per term (hi*hi + hi*lo + lo*hi) bring the search to ~2^-17 relative
+// accuracy for the cost of one extra K = 16 slice at g = 4 and none at g <= 2.
+__host__ __device__ constexpr bool gq_split_image(int g) { return g <= 4; }
+__host__ __device__ constexpr int gq_image_k(int g) { return gq_split_image(g) ? 6 * g : 2 * g; }
+__host__ __device__ constexpr int gq_image_kpad(int g) { return (gq_image_k(g) + 15) / 16 * 16; }
+
 // opaque handle behind gq_codebook_t
 struct gq_codebook {
     int64_t N;        // codewords
     int g;            // group (dims per codeword)
-    int kpad;         // K of the fp16 operand image (2g rounded up to a multiple of 16)
+    int kpad;         // K of the fp16 operand image (gq_image_kpad(g))
     int64_t n_pad;    // N rounded up to the search tile
     float beta;
     void *base;       // the single device allocation

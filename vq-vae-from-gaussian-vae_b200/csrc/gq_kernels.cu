@@ -359,7 +359,8 @@ int launch_exact_sliced(const gq_codebook *cb, const float *mu, const float *std
 // Codebook preparation (once per codebook, off the hot path).
 //   nlpb[n,k] = nlp[n,k]*beta (one fp32 rounding, gaussian.py:143-144); nlp itself, when not
 //   supplied, is Normal(0,1).log_prob(x) in torch's op order (gaussian.py:51-52).
-//   bimg: fp16 [x^2 | x | 0-pad] rows of K = kpad, stored in UMMA K-major no-swizzle
+//   bimg: fp16 [x^2 | x | 0-pad] rows of K = kpad (split-precision variant for g <= 4, see gq_common.cuh),
+//   stored in UMMA K-major no-swizzle
 //   core-matrix order: byte(n,k) = (n/8)*(kpad/8)*128 + (k/8)*128 + (n%8)*16 + (k%8)*2.
 //   Rows n >= N (tile padding) are zero except k==2g slot... they are masked in the epilogue.
 //   meta[0] = max_n ||x_n||^2 , meta[1] = sqrt(meta[0]), meta[2+j] = max_n |B[n,j]|,
@@ -375,13 +376,19 @@ __global__ void codebook_prep_kernel(const float *__restrict__ cb, const float *
     const int kch = kpad / 8;
     char *rowbase = reinterpret_cast<char *>(bimg) + (n / 8) * (int64_t)kch * 128 + (n % 8) * 16;
     float nrm2 = 0.f;
+    const bool split = gq_split_image(g);
     for (int k = 0; k < kpad; ++k) {
+        // column k of the image: plain image [x^2 | x | 0]; split image [hi(x^2|x) | lo(x^2|x) | hi(x^2|x) | 0],
+        // paired with the row image [hi | hi | lo] (gq_tc.cu prep_row), lo = fp16(v - fp16(v))
+        const int part = split ? k / (2 * g) : 0;
+        const int j = split ? k % (2 * g) : k;
         float v = 0.f;
-        if (n < N) {
-            if (k < g) { float x = cb[n * g + k]; v = __fmul_rn(x, x); nrm2 += v; }
-            else if (k < 2 * g) v = cb[n * g + (k - g)];
+        if (n < N && (split ? part < 3 : k < 2 * g)) {
+            if (j < g) { float x = cb[n * g + j]; v = __fmul_rn(x, x); if (part == 0) nrm2 += v; }
+            else v = cb[n * g + (j - g)];
         }
         __half h = __float2half_rn(v);
+        if (split && part == 1) h = __float2half_rn(__fsub_rn(v, __half2float(h)));
         *reinterpret_cast<__half *>(rowbase + (k / 8) * 128 + (k % 8) * 2) = h;
         if (n < N && k < 2 * g) {
             // max over the *rounded* operand magnitudes and the exact ones

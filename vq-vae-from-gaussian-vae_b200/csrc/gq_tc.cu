@@ -249,26 +249,36 @@ __device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G
         const float p_norm = amax * meta[0] + sqrtf(bnorm2) * 1.000001f * meta[1];
         const float P = fminf(p_naive, p_norm);
         const float sumB = meta[2 + 2 * kMaxG];
-        const float e_tc = 1.01f * ldexpf(P, -10) + ldexpf(sumB / scale + sumA, -25) + ldexpf(eA, -22);
+        // plain image: fp16 rounding of both operands dominates.  Split image (g <= 4): what is left is
+        // the rounding of the two lo parts (2^-22 each), the dropped lo*lo product (2^-22) and the tensor
+        // core's fp32 accumulation of up to 32 products, bounded by 2^-18 P (32 truncating adds of 2^-23
+        // relative each; measured worst case on B200 is 25x below the resulting window: scripts/tc_diag.py
+        // dump_g4 reports max |error| / (W/2) = 0.02 with the 2^-17 variant of this bound).
+        const float e_round = gq_split_image(G) ? 1.01f * (ldexpf(P, -18) + ldexpf(P, -20)) : 1.01f * ldexpf(P, -10);
+        const float e_floor = ldexpf(sumB / scale + sumA, gq_split_image(G) ? -24 : -25);   // fp16 subnormal floors (hi and lo parts)
+        const float e_tc = e_round + e_floor + ldexpf(eA, -22);
         constexpr float kE = (G > 16) ? 2.0f : 1.0f;   // deeper fp32 summation trees for g = 32
         const float W = 2.02f * (e_tc + kE * ldexpf(R, -20));
         margin = 2.02f * kE * 4.0f * ldexpf(R, -20);
         if (!(W <= w_max) || !isfinite(W * scale)) bad = true;
         else w_scaled = W * scale * 1.001f;
     }
-    // fp16 row, 16-byte stores
+    // fp16 row, 16-byte stores.  Plain image: [A | 0]; split image: [hi(A) | hi(A) | lo(A) | 0].
+    auto image_value = [&](int k) -> float {
+        if (bad) return 0.f;
+        if (!gq_split_image(G)) return k < 2 * G ? A[k < 2 * G ? k : 0] * scale : 0.f;
+        const int part = k / (2 * G), j = k % (2 * G);
+        if (part >= 3) return 0.f;
+        const float v = A[j] * scale;                                   // exact: scale is a power of two
+        const float hi = __half2float(__float2half_rn(v));
+        return part == 2 ? __fsub_rn(v, hi) : hi;                       // v - hi is exact in fp32
+    };
     uint4 *dst = reinterpret_cast<uint4 *>(a_row);
 #pragma unroll
     for (int c = 0; c < KPAD / 8; ++c) {
         __half2 h[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k0 = c * 8 + 2 * i;
-            float v0 = 0.f, v1 = 0.f;
-            if (k0 < 2 * G) v0 = bad ? 0.f : A[k0 < 2 * G ? k0 : 0] * scale;
-            if (k0 + 1 < 2 * G) v1 = bad ? 0.f : A[k0 + 1 < 2 * G ? k0 + 1 : 0] * scale;
-            h[i] = __floats2half2_rn(v0, v1);
-        }
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(image_value(c * 8 + 2 * i), image_value(c * 8 + 2 * i + 1));
         dst[c] = *reinterpret_cast<uint4 *>(h);
     }
     *w_out = w_scaled;
@@ -1247,7 +1257,7 @@ int launch_quantize_latent(const gq_codebook *cb, const float *z, const float *e
     switch (cb->g) {
     case 1: GQ_LAT(1, 16);
     case 2: GQ_LAT(2, 16);
-    case 4: GQ_LAT(4, 16);
+    case 4: GQ_LAT(4, 32);
     case 8: GQ_LAT(8, 16);
     case 16: GQ_LAT(16, 32);
     case 32: GQ_LAT(32, 64);
@@ -1282,7 +1292,7 @@ int launch_quantize_tc(const gq_codebook *cb, const float *mu, const float *std,
     switch (cb->g) {
     case 1: return run_tc<1, 16>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
     case 2: return run_tc<2, 16>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
-    case 4: return run_tc<4, 16>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
+    case 4: return run_tc<4, 32>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
     case 8: return run_tc<8, 16>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
     case 16: return run_tc<16, 32>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
     case 32: return run_tc<32, 64>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
@@ -1298,7 +1308,7 @@ int debug_tc_scores(const gq_codebook *cb, const float *mu, const float *std, co
     TcWorkspace w = carve(cb, p, ws);
     if (ws == nullptr || ws_bytes < w.bytes) { set_error("workspace too small"); return GQ_ERR_WORKSPACE; }
     switch (cb->g) {
-    case 4: return run_tc_dump<4, 16>(cb, mu, std, lstd, M, p, w, dump, wrow_out, g_w_max, stream);
+    case 4: return run_tc_dump<4, 32>(cb, mu, std, lstd, M, p, w, dump, wrow_out, g_w_max, stream);
     case 8: return run_tc_dump<8, 16>(cb, mu, std, lstd, M, p, w, dump, wrow_out, g_w_max, stream);
     case 16: return run_tc_dump<16, 32>(cb, mu, std, lstd, M, p, w, dump, wrow_out, g_w_max, stream);
     default: set_error("debug dump supports g in {4,8,16}"); return GQ_ERR_INVALID;
