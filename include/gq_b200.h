@@ -156,7 +156,7 @@ int gq_kl_bwd(const float *z, const float *eps, const float *w, const float *gra
               int layout, float lv_lo, float lv_hi, float lam, gq_stream_t stream);
 
 /* ---- measurement and diagnostics (no reference counterpart) ------------------------------
- * gq_profile_enable(1): every later gq_quantize records a CUDA-event pair around its search
+ * gq_profile_enable(n): every n-th later gq_quantize (n = 1: every one; 0: off) records a CUDA-event pair around its search
  * kernel on the caller's stream; gq_profile_read sums and clears them (synchronises on the
  * recorded events).  gq_set_window_max: rows whose rigorous error window exceeds `w` (score
  * units) go to the exact scan (default 3.0).  gq_debug_tc_scores dumps the raw tensor-core
@@ -165,6 +165,9 @@ int gq_kl_bwd(const float *z, const float *eps, const float *w, const float *gra
 void gq_profile_enable(int on);
 int gq_profile_read(double *total_ms, int *count);
 void gq_set_window_max(float w);
+/* The kernels of one gq_quantize* call are chained with programmatic dependent launch (each starts
+ * with griddepcontrol.wait); gq_set_chained_launch(0) falls back to plain stream order (default 1). */
+void gq_set_chained_launch(int on);
 int gq_debug_tc_scores(const gq_codebook_t *cb, const float *mu, const float *std,
                        const float *log_std, int64_t M, void *workspace, int64_t workspace_bytes,
                        float *dump, float *wrow_out, gq_stream_t stream);

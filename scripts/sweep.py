@@ -20,10 +20,18 @@ import oracle  # noqa: E402
 from gq_b200_host import host_codebook  # noqa: E402
 
 
-def rows(M, g, seed):
+def rows(M, g, seed, dist="trained"):
+    """The three named latent distributions of SURVEY 8(d)."""
     gen = torch.Generator().manual_seed(seed)
-    mu = torch.randn(M, g, generator=gen) * 0.866           # D-trained latents
-    lv = -1.386 + 0.3 * torch.randn(M, g, generator=gen)
+    if dist == "trained":       # what a converged model emits: ~16 bits per 16-dim group
+        mu = torch.randn(M, g, generator=gen) * 0.866
+        lv = -1.386 + 0.3 * torch.randn(M, g, generator=gen)
+    elif dist == "randinit":    # what the random-init UNet of configs[1] emits
+        mu = torch.randn(M, g, generator=gen) * 0.34
+        lv = torch.randn(M, g, generator=gen) * 0.34
+    else:                       # "stress": gq_cuda_extension/test/test_extension.py:18-19, std = |N(0,1)|
+        mu = torch.randn(M, g, generator=gen)
+        lv = 2.0 * torch.log(torch.abs(torch.randn(M, g, generator=gen)) + 1e-3)
     std = torch.exp(0.5 * lv)
     return mu, std, std.log()
 
@@ -37,23 +45,25 @@ def main():
         peak = float(d.get("bf16_tflops", d.get("tensor_tflops", peak)))
     dev = torch.device("cuda:0")
     points = []
-    grid = [(16, N, M) for N in (4096, 16384, 65536, 262144) for M in (1024, 16384, 65536, 262144, 1048576)]
-    grid += [(4, 65536, 1048576), (8, 65536, 524288), (4, 65536, 65536), (8, 65536, 65536)]   # configs[2]-style sub-codebooks
+    grid = [(16, N, M, "trained") for N in (4096, 16384, 65536, 262144) for M in (1024, 16384, 65536, 262144, 1048576)]
+    grid += [(4, 65536, 1048576, "trained"), (8, 65536, 524288, "trained"), (4, 65536, 65536, "trained"),
+             (8, 65536, 65536, "trained")]                                     # configs[2]-style sub-codebooks
+    grid += [(16, 65536, 65536, "randinit"), (16, 65536, 65536, "stress"), (16, 65536, 8192, "stress")]
     if quick:
-        grid = [(16, 65536, 65536), (4, 65536, 65536)]
+        grid = [(16, 65536, 65536, "trained"), (4, 65536, 65536, "trained"), (16, 65536, 8192, "stress")]
     cbs = {}
-    for g, N, M in grid:
+    for g, N, M, dist in grid:
         if (N, g) not in cbs:
             cbn, nlp = host_codebook(N, g)
             cbs[(N, g)] = (cbn, nlp, gq_b200.Codebook(torch.from_numpy(cbn).to(dev), torch.from_numpy(nlp).to(dev), 1.0))
         cbn, nlp, cb = cbs[(N, g)]
-        mu, std, lstd = rows(M, g, N % 1000 + M % 1000 + g)
+        mu, std, lstd = rows(M, g, N % 1000 + M % 1000 + g, dist)
         mu_d, std_d, lstd_d = mu.to(dev), std.to(dev), lstd.to(dev)
         stats = torch.zeros(8, dtype=torch.int32, device=dev)
         for _ in range(3):
             idx, zhat = gq_b200.quantize_rows(cb, mu_d, std_d, lstd_d)
         torch.cuda.synchronize()
-        iters = 5 if M * N >= (1 << 36) else 20
+        iters = 5 if (M * N >= (1 << 36) or dist == "stress") else 20
         ts = []
         for _ in range(iters):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -69,7 +79,7 @@ def main():
         mism = int((idx.cpu().numpy()[sel] != o_idx).sum())
         flop = 4.0 * g * M * N
         st = stats.cpu().tolist()
-        points.append({"g": g, "N": N, "M": M, "ms": ms, "rows_per_s": M / ms * 1e3, "tflops": flop / ms / 1e9,
+        points.append({"g": g, "N": N, "M": M, "latents": dist, "ms": ms, "rows_per_s": M / ms * 1e3, "tflops": flop / ms / 1e9,
                        "frac_of_tensor_peak": flop / ms / 1e9 / peak, "rows_checked": int(len(sel)), "index_mismatches": mism,
                        "rows_to_exact_scan": st[2], "rows_settled_in_exact_order": st[4]})
         print(points[-1], file=sys.stderr, flush=True)

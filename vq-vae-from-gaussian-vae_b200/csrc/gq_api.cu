@@ -58,9 +58,12 @@ static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * 
 
 using namespace gq;
 
+namespace gq { bool g_chained_launch = true; }
+
 extern "C" {
 
 int gq_abi_version(void) { return GQ_B200_ABI_VERSION; }
+void gq_set_chained_launch(int on) { gq::g_chained_launch = on != 0; }
 const char *gq_last_error(void) { return g_err; }
 uint64_t gq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

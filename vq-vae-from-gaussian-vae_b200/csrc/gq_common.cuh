@@ -104,6 +104,37 @@ __host__ __device__ constexpr bool gq_split_image(int g) { return g <= 4; }
 __host__ __device__ constexpr int gq_image_k(int g) { return gq_split_image(g) ? 6 * g : 2 * g; }
 __host__ __device__ constexpr int gq_image_kpad(int g) { return (gq_image_k(g) + 15) / 16 * 16; }
 
+namespace gq {
+extern bool g_chained_launch;   // gq_api.cu; gq_set_chained_launch()
+
+// ---- programmatic dependent launch ----------------------------------------------------------------
+// The step is a chain of dependent kernels on one stream.  Each is launched with the
+// programmatic-stream-serialization attribute and starts with griddepcontrol.wait, so the GPU can set
+// the next grid up while the previous one drains instead of paying a launch gap per boundary; nothing
+// produced by the predecessor is touched before the wait.  griddepcontrol.launch_dependents is issued
+// where letting the successor's CTAs become resident cannot starve the kernel's own later waves.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_chained_launch ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+}  // namespace gq
+
 // opaque handle behind gq_codebook_t
 struct gq_codebook {
     int64_t N;        // codewords

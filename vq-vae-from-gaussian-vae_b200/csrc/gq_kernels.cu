@@ -240,6 +240,7 @@ exact_sliced_kernel(const float *__restrict__ mu, const float *__restrict__ std,
                     unsigned long long *__restrict__ keys, uint32_t *__restrict__ done,
                     int64_t *__restrict__ idx_out, float *__restrict__ zhat_out)
 {
+    pdl_wait();   // launched as a programmatic dependent of settle_kernel (gq_tc.cu run_tc)
     __shared__ float s_mu[kExactRows][G], s_den[kExactRows][G], s_ls[kExactRows][G];
     __shared__ int64_t s_row[kExactRows];
     __shared__ unsigned long long s_key[kExactRows][kExactThreads / 32];
@@ -339,8 +340,8 @@ int launch_exact_sliced(const gq_codebook *cb, const float *mu, const float *std
     (void)M;
     const int slices = (int)imax(1, imin(64, cb->N / 1024));
     const int blocks = device_sm_count() * 4;
-#define GQ_XS(GG) exact_sliced_kernel<GG><<<blocks, kExactThreads, 0, stream>>>(mu, std, lstd, cb->cb, cb->nlpb, cb->N, \
-        row_list, row_count, slices, keys, done, idx, zhat)
+#define GQ_XS(GG) launch_chained(exact_sliced_kernel<GG>, dim3(blocks), dim3(kExactThreads), 0, stream, mu, std, lstd, cb->cb, \
+        cb->nlpb, cb->N, row_list, row_count, slices, keys, done, idx, zhat)
     switch (cb->g) {
     case 1: GQ_XS(1); break;
     case 2: GQ_XS(2); break;

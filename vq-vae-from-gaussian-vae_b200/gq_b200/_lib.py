@@ -60,6 +60,7 @@ PROTOTYPES = {
     "gq_profile_enable": (None, [c_int]),
     "gq_profile_read": (c_int, [POINTER(c_double), POINTER(c_int)]),
     "gq_set_window_max": (None, [c_float]),
+    "gq_set_chained_launch": (None, [c_int]),
     "gq_debug_tc_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_void_p]),
     "gq_debug_plan": (None, [c_int64, c_int64, c_int, POINTER(c_int64)]),
@@ -87,6 +88,8 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = args
         if l.gq_abi_version() != ABI_VERSION:
             raise ImportError(f"libgq_b200 ABI {l.gq_abi_version()} != expected {ABI_VERSION}")
+        if os.environ.get("GQ_B200_CHAINED_LAUNCH", "1") == "0":     # diagnostics: plain stream order
+            l.gq_set_chained_launch(0)
         _lib = l
     return _lib
 
