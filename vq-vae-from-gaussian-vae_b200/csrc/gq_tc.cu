@@ -441,10 +441,11 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     const int64_t step_begin = (int64_t)cta * steps_per_cta;
     const int64_t step_end = imin(step_begin + steps_per_cta, total_steps);
     mbar_probe_declare();
-    // one persistent wave: the successor's CTAs cannot become resident before these exit anyway, so its
-    // launch may be set up at once; nothing the predecessor wrote is read before the wait
+    // One persistent wave: the successor's CTAs cannot become resident before these exit anyway, so its
+    // launch may be set up at once.  Barrier init, the TMEM allocation and the first codebook tiles (static
+    // data) do not depend on the predecessor and overlap its tail; only the epilogue warps consume what
+    // it wrote (row operands, windows, initialised segment headers) and wait for it below.
     pdl_launch_dependents();
-    pdl_wait();
     GQ_TRACE_DECL();
 
     if (warp == kIssuerWarp0 && lane == 0) {
@@ -569,6 +570,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         int cur = 0;   // 0: the next use takes stage A, 1: stage B
         int pad_tile;   // pinned in a register (otherwise re-derived from the kernel parameters every tile)
         asm volatile("mov.b32 %0, %1;" : "=r"(pad_tile) : "r"(padded ? tiles - 1 : -1));
+        pdl_wait();     // the predecessor's rows / windows / segment headers are complete and visible from here on
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
             const int64_t row = (int64_t)p.unit * kUnitRows + rb * kBlockRows + q * 32 + lane;
             const int sseg = p.seg * kHalves + half;
