@@ -52,6 +52,14 @@ typedef enum gq_status {
     GQ_ERR_WORKSPACE = -4    /* workspace too small */
 } gq_status;
 
+/* Search precision of a codebook with group 8 or 16 (other groups ignore it).  FAST: fp16 operand
+ * image; rows whose error window is too wide (very small variances) take the exact CUDA-core scan.
+ * ROBUST: split-precision image (three fp16 products per term, K = 6g), ~1.4x the search time, windows
+ * ~250x tighter.  AUTO (default): FAST until a completed call on this codebook had more than 1/16 of
+ * its rows over the window cap, ROBUST while that stays true (the count is computed in both modes and
+ * read from pinned host memory without synchronising, so the switch lags by a call or two). */
+enum gq_mode { GQ_MODE_AUTO = 0, GQ_MODE_FAST = 1, GQ_MODE_ROBUST = 2 };
+
 /* tensor layouts of the regularizer's latent / index tensors (gaussian.py:33,65-74) */
 typedef enum gq_layout {
     GQ_LAYOUT_BLC = 0, /* [b, l, c]      channel innermost */
@@ -77,6 +85,7 @@ typedef struct gq_codebook gq_codebook_t;
 int gq_codebook_create(const float *codebook, const float *nlp, int64_t N, int g, float beta,
                        gq_stream_t stream, gq_codebook_t **out);
 void gq_codebook_destroy(gq_codebook_t *cb);
+int gq_codebook_set_mode(gq_codebook_t *cb, int mode);
 int64_t gq_codebook_size(const gq_codebook_t *cb);
 int gq_codebook_group(const gq_codebook_t *cb);
 const float *gq_codebook_data(const gq_codebook_t *cb); /* device fp32 [N,g] */

@@ -138,3 +138,6 @@ def test_index_stream_entry_points_validate_without_gpu(lib):
     d.restype = ctypes.c_int
     d.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     assert d(None, None, None, 1, 1, 1, 0, None, None) == -1 and b"handle is null" in lib.gq_last_error()
+    m = lib.gq_codebook_set_mode
+    m.restype, m.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]
+    assert m(None, 0) == -1 and b"handle is null" in lib.gq_last_error()

@@ -460,6 +460,45 @@ def test_quantize_many_units_ragged_vs_oracle(gq, N, g, M):
     assert np.array_equal(zhat.cpu().numpy(), o_zhat)
 
 
+@pytest.mark.parametrize("N,g,M", [(4096, 16, 3000), (65536, 16, 2048), (4096, 8, 1500)])
+def test_search_modes_agree_on_low_variance_rows(gq, N, g, M):
+    """The 'stress' latents of the reference's extension test (std = |N(0,1)|, test_extension.py:18-19):
+    most rows have a too-wide fp16 window.  fast mode sends them to the exact scan, robust mode keeps
+    them on the tensor cores with the split-precision image, auto switches after it has seen a call;
+    the indices are identical (and equal to the oracle's) in every mode."""
+    cbn = np.asarray(big_codebook(gq, N, g)[0].numpy())
+    nlp = oracle.normal_log_prob(cbn)
+    h = gq.Codebook(dev(cbn), dev(nlp), 1.0)          # private handle: the mode is per codebook
+    mu, std, lstd = trained_rows(M, g, seed=5, dist="stress")
+    o_idx, o_zhat, _, gap = oracle.quantize(mu.numpy(), std.numpy(), lstd.numpy(), cbn, nlp)
+    res = {}
+    for mode in ("fast", "robust"):
+        h.set_mode(mode)
+        stats = torch.zeros(8, dtype=torch.int32, device="cuda")
+        idx, zhat = gq.quantize_rows(h, mu.cuda(), std.cuda(), lstd.cuda(), stats=stats)
+        bad = np.nonzero(idx.cpu().numpy() != o_idx)[0]
+        assert len(bad) == 0, f"{mode}: {len(bad)} mismatches, gaps {gap[bad][:5]}"
+        assert np.array_equal(zhat.cpu().numpy(), o_zhat)
+        res[mode] = int(stats[2])                      # rows that went to the exact scan
+    assert res["fast"] > M // 4                        # the distribution does what it is meant to
+    assert res["robust"] < res["fast"] // 4            # and the split image takes most of them (std < ~0.01 stays out)
+    h.set_mode("auto")
+    for call in range(3):                              # feedback arrives with the completed call
+        stats = torch.zeros(8, dtype=torch.int32, device="cuda")
+        idx, _ = gq.quantize_rows(h, mu.cuda(), std.cuda(), lstd.cuda(), stats=stats)
+        torch.cuda.synchronize()
+        assert np.array_equal(idx.cpu().numpy(), o_idx)
+    assert int(stats[2]) == res["robust"]              # auto has switched to the robust image
+    # and back: well-conditioned rows clear the feedback again
+    mu2, std2, lstd2 = trained_rows(M, g, seed=6)
+    for call in range(3):
+        gq.quantize_rows(h, mu2.cuda(), std2.cuda(), lstd2.cuda())
+        torch.cuda.synchronize()
+    stats = torch.zeros(8, dtype=torch.int32, device="cuda")
+    idx, _ = gq.quantize_rows(h, mu.cuda(), std.cuda(), lstd.cuda(), stats=stats)
+    assert np.array_equal(idx.cpu().numpy(), o_idx) and int(stats[2]) == res["fast"]
+
+
 def test_quantize_degenerate_rows(gq):
     """Rows the search cannot certify must still come out as the exact scan would give them:
     tiny variances (window too wide), huge variances, duplicate codewords (exact ties -> first

@@ -113,8 +113,12 @@ int gq_codebook_create(const float *codebook, const float *nlp, int64_t N, int g
     int64_t off_cb = 0;
     int64_t off_nlpb = align_up(off_cb + N * g * 4, 256);
     int64_t off_bimg = align_up(off_nlpb + N * g * 4, 256);
-    int64_t off_meta = align_up(off_bimg + cb->n_pad * cb->kpad * 2, 256);
-    int64_t total = off_meta + 4 * (2 + 2 * kMaxG) + 256;
+    cb->kpad_robust = gq_has_robust_image(g) ? gq_image_kpad(g, true) : 0;
+    cb->mode = GQ_MODE_AUTO;
+    int64_t off_bimg2 = align_up(off_bimg + cb->n_pad * cb->kpad * 2, 256);
+    int64_t off_meta = align_up(off_bimg2 + cb->n_pad * cb->kpad_robust * 2, 256);
+    int64_t off_wide = align_up(off_meta + 4 * (3 + 2 * kMaxG), 256);
+    int64_t total = off_wide + 256;
     cudaError_t e = cudaMalloc(&cb->base, (size_t)total);
     if (e != cudaSuccess) { set_error("gq_codebook_create: cudaMalloc(%lld): %s", (long long)total, cudaGetErrorString(e)); delete cb; return GQ_ERR_CUDA; }
     char *b = reinterpret_cast<char *>(cb->base);
@@ -122,6 +126,24 @@ int gq_codebook_create(const float *codebook, const float *nlp, int64_t N, int g
     cb->nlpb = reinterpret_cast<float *>(b + off_nlpb);
     cb->bimg = reinterpret_cast<__half *>(b + off_bimg);
     cb->meta = reinterpret_cast<float *>(b + off_meta);
+    cb->bimg_robust = cb->kpad_robust ? reinterpret_cast<__half *>(b + off_bimg2) : nullptr;
+    cb->wide_dev = reinterpret_cast<uint32_t *>(b + off_wide);
+    // feedback word for GQ_MODE_AUTO: pinned + mapped, written by the last kernel of a call, read by the
+    // host when it sets up the next one (never synchronised on)
+    cb->fb_host = nullptr;
+    cb->fb_dev = nullptr;
+    {
+        void *h = nullptr, *d = nullptr;
+        if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+            memset(h, 0, 64);
+            cb->fb_host = static_cast<volatile uint32_t *>(h);
+            cb->fb_dev = static_cast<uint32_t *>(d);
+        } else {
+            if (h) cudaFreeHost(h);
+            (void)cudaGetLastError();   // no feedback: AUTO behaves like FAST
+        }
+    }
+    cudaMemsetAsync(cb->wide_dev, 0, 256, (cudaStream_t)stream);
     e = cudaMemcpyAsync(cb->cb, codebook, (size_t)(N * g * 4), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     if (e != cudaSuccess) { set_error("gq_codebook_create: copy: %s", cudaGetErrorString(e)); cudaFree(cb->base); delete cb; return GQ_ERR_CUDA; }
     int rc = launch_codebook_prep(cb, nlp, (cudaStream_t)stream);
@@ -134,7 +156,16 @@ void gq_codebook_destroy(gq_codebook_t *cb)
 {
     if (!cb) return;
     cudaFree(cb->base);
+    if (cb->fb_host) cudaFreeHost(const_cast<uint32_t *>(cb->fb_host));
     delete cb;
+}
+
+int gq_codebook_set_mode(gq_codebook_t *cb, int mode)
+{
+    if (!cb) { set_error("gq_codebook_set_mode: codebook handle is null"); return GQ_ERR_INVALID; }
+    if (mode != GQ_MODE_AUTO && mode != GQ_MODE_FAST && mode != GQ_MODE_ROBUST) { set_error("gq_codebook_set_mode: bad mode %d", mode); return GQ_ERR_INVALID; }
+    cb->mode = mode;
+    return GQ_OK;
 }
 
 int64_t gq_codebook_size(const gq_codebook_t *cb) { return cb ? cb->N : 0; }

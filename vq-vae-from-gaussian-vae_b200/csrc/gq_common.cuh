@@ -100,9 +100,16 @@ __device__ __forceinline__ void load_row(const float *__restrict__ p, float (&v)
 // 65 536 points is so dense that hundreds of codewords fall inside the fp16 error window of the best
 // one.  Three fp16 products per term (hi*hi + hi*lo + lo*hi) bring the search to ~2^-17 relative
 // accuracy for the cost of one extra K = 16 slice at g = 4 and none at g <= 2.
-__host__ __device__ constexpr bool gq_split_image(int g) { return g <= 4; }
-__host__ __device__ constexpr int gq_image_k(int g) { return gq_split_image(g) ? 6 * g : 2 * g; }
-__host__ __device__ constexpr int gq_image_kpad(int g) { return (gq_image_k(g) + 15) / 16 * 16; }
+//
+// g = 8 and g = 16 normally use the plain image (their windows are tight enough for typical latents), but
+// rows with very small variances blow the fp16 window up and would fall back to the CUDA-core exact
+// scan.  For those groups a second, split-precision image ("robust" mode, K = 6g = 48 / 96) is kept and
+// a call switches to it when the previous calls on the codebook saw many such rows (gq_codebook_set_mode).
+__host__ __device__ constexpr bool gq_split_image(int g) { return g <= 4; }                     // always split
+__host__ __device__ constexpr bool gq_has_robust_image(int g) { return g == 8 || g == 16; }    // optional split
+__host__ __device__ constexpr int gq_image_k(int g, bool split) { return split ? 6 * g : 2 * g; }
+__host__ __device__ constexpr int gq_image_kpad(int g, bool split) { return (gq_image_k(g, split) + 15) / 16 * 16; }
+__host__ __device__ constexpr int gq_image_kpad(int g) { return gq_image_kpad(g, gq_split_image(g)); }
 
 namespace gq {
 extern bool g_chained_launch;   // gq_api.cu; gq_set_chained_launch()
@@ -148,4 +155,11 @@ struct gq_codebook {
     __half *bimg;     // fp16 operand image, UMMA K-major no-swizzle core-matrix order
     float *meta;      // device floats: [0]=max ||x||^2, [1]=max ||x||, [2..2+2g) per-column max |B|, [2+2*kMaxG] their sum
     int device;
+    // robust mode (g = 8, 16): split-precision image and the feedback that drives GQ_MODE_AUTO
+    int kpad_robust;          // 0 when the group has no robust image
+    __half *bimg_robust;
+    int mode;                 // gq_mode
+    uint32_t *wide_dev;       // device word: rows of the calls in flight whose PLAIN window exceeded the cap
+    volatile uint32_t *fb_host;   // pinned, mapped: [0] = such rows in the last completed call, [1] = its row count
+    uint32_t *fb_dev;         // device view of fb_host
 };

@@ -238,9 +238,17 @@ exact_sliced_kernel(const float *__restrict__ mu, const float *__restrict__ std,
                     const float *__restrict__ cb, const float *__restrict__ nlpb, int64_t N,
                     const uint32_t *__restrict__ row_list, const uint32_t *__restrict__ row_count, int slices,
                     unsigned long long *__restrict__ keys, uint32_t *__restrict__ done,
-                    int64_t *__restrict__ idx_out, float *__restrict__ zhat_out)
+                    int64_t *__restrict__ idx_out, float *__restrict__ zhat_out, uint32_t *__restrict__ wide_dev,
+                    uint32_t *__restrict__ fb_dev, uint32_t rows_total)
 {
     pdl_wait();   // launched as a programmatic dependent of settle_kernel (gq_tc.cu run_tc)
+    // last kernel of the call: publish how many of its rows had a plain-image window over the cap
+    // (GQ_MODE_AUTO feedback, read by the host without synchronising) and reset the device word
+    if (fb_dev && blockIdx.x == 0 && threadIdx.x == 0) {
+        fb_dev[0] = atomicExch(wide_dev, 0u);
+        fb_dev[1] = rows_total;
+        __threadfence_system();
+    }
     __shared__ float s_mu[kExactRows][G], s_den[kExactRows][G], s_ls[kExactRows][G];
     __shared__ int64_t s_row[kExactRows];
     __shared__ unsigned long long s_key[kExactRows][kExactThreads / 32];
@@ -337,11 +345,11 @@ int launch_exact_sliced(const gq_codebook *cb, const float *mu, const float *std
                         const uint32_t *row_list, const uint32_t *row_count, unsigned long long *keys,
                         uint32_t *done, int64_t *idx, float *zhat, cudaStream_t stream)
 {
-    (void)M;
     const int slices = (int)imax(1, imin(64, cb->N / 1024));
     const int blocks = device_sm_count() * 4;
 #define GQ_XS(GG) launch_chained(exact_sliced_kernel<GG>, dim3(blocks), dim3(kExactThreads), 0, stream, mu, std, lstd, cb->cb, \
-        cb->nlpb, cb->N, row_list, row_count, slices, keys, done, idx, zhat)
+        cb->nlpb, cb->N, row_list, row_count, slices, keys, done, idx, zhat, cb->wide_dev, cb->fb_dev, \
+        (uint32_t)imin(M, (int64_t)0xffffffffll))
     switch (cb->g) {
     case 1: GQ_XS(1); break;
     case 2: GQ_XS(2); break;
@@ -370,14 +378,14 @@ int launch_exact_sliced(const gq_codebook *cb, const float *mu, const float *std
 __global__ void codebook_prep_kernel(const float *__restrict__ cb, const float *__restrict__ nlp_in,
                                      float *__restrict__ nlpb, __half *__restrict__ bimg,
                                      float *__restrict__ meta, int64_t N, int64_t n_pad, int g, int kpad,
-                                     float beta)
+                                     float beta, int split_image, int primary)
 {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n_pad) return;
     const int kch = kpad / 8;
     char *rowbase = reinterpret_cast<char *>(bimg) + (n / 8) * (int64_t)kch * 128 + (n % 8) * 16;
     float nrm2 = 0.f;
-    const bool split = gq_split_image(g);
+    const bool split = split_image != 0;
     for (int k = 0; k < kpad; ++k) {
         // column k of the image: plain image [x^2 | x | 0]; split image [hi(x^2|x) | lo(x^2|x) | hi(x^2|x) | 0],
         // paired with the row image [hi | hi | lo] (gq_tc.cu prep_row), lo = fp16(v - fp16(v))
@@ -391,13 +399,13 @@ __global__ void codebook_prep_kernel(const float *__restrict__ cb, const float *
         __half h = __float2half_rn(v);
         if (split && part == 1) h = __float2half_rn(__fsub_rn(v, __half2float(h)));
         *reinterpret_cast<__half *>(rowbase + (k / 8) * 128 + (k % 8) * 2) = h;
-        if (n < N && k < 2 * g) {
+        if (primary && n < N && k < 2 * g) {
             // max over the *rounded* operand magnitudes and the exact ones
             float a = fmaxf(fabsf(v), fabsf(__half2float(h)));
             atomicMax(reinterpret_cast<int *>(meta + 2 + k), __float_as_int(a));
         }
     }
-    if (n < N) {
+    if (primary && n < N) {
         atomicMax(reinterpret_cast<int *>(meta + 0), __float_as_int(nrm2));
         for (int k = 0; k < g; ++k) {
             float x = cb[n * g + k];
@@ -427,9 +435,15 @@ int launch_codebook_prep(gq_codebook *cb, const float *nlp_in, cudaStream_t stre
     if (e != cudaSuccess) { set_error("memset meta: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
     int64_t blocks = (cb->n_pad + 255) / 256;
     codebook_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(cb->cb, nlp_in, cb->nlpb, cb->bimg, cb->meta,
-                                                               cb->N, cb->n_pad, cb->g, cb->kpad, cb->beta);
+                                                               cb->N, cb->n_pad, cb->g, cb->kpad, cb->beta,
+                                                               gq_split_image(cb->g) ? 1 : 0, 1);
     codebook_meta_finish_kernel<<<1, 1, 0, stream>>>(cb->meta, cb->g);
     count_launch(2);
+    if (cb->kpad_robust) {   // second, split-precision image for the robust mode (nlpb / meta already written)
+        codebook_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(cb->cb, nlp_in, cb->nlpb, cb->bimg_robust, cb->meta,
+                                                                   cb->N, cb->n_pad, cb->g, cb->kpad_robust, cb->beta, 1, 0);
+        count_launch(1);
+    }
     return check_launch("codebook_prep_kernel");
 }
 

@@ -77,7 +77,7 @@ using namespace gq::ptx;
 constexpr int kTileN = 128;          // codewords per B tile / MMA N
 constexpr int kBlockRows = 128;      // rows per MMA (M)
 constexpr int kUnitRows = 256;       // rows per CTA work unit (two row blocks)
-constexpr int kStages = 8;           // B ring depth
+constexpr int kMaxStages = 8;        // codebook-tile ring depth (6 for the 24 KB tiles of the K = 96 image)
 constexpr int kAccStages = 4;        // TMEM accumulator stages: two private ones per row block (rb, rb + 2)
 constexpr int kTmemCols = 512;       // 4 x 128 accumulator columns (the row operands live in shared memory)
 #ifndef GQ_EPI_HALVES
@@ -161,7 +161,7 @@ static TcWorkspace carve(const gq_codebook *cb, const TcPlan &p, void *base)
     char *ptr = reinterpret_cast<char *>(base);
     int64_t off = 0;
     w.a_img = reinterpret_cast<__half *>(ptr + off);
-    off = align_up(off + p.M_pad * cb->kpad * 2, 256);
+    off = align_up(off + p.M_pad * imax(cb->kpad, cb->kpad_robust) * 2, 256);
     w.wrow = reinterpret_cast<float *>(ptr + off);
     off = align_up(off + p.M_pad * 4, 256);
     w.margin = reinterpret_cast<float *>(ptr + off);
@@ -207,12 +207,12 @@ int64_t tc_workspace_bytes(const gq_codebook *cb, int64_t M)
 //   W     = 2 * (E_tc + E_ref)                  (x 1.01: the bound itself is evaluated in fp32)
 //   E_pre = 3 * 2^-20 * R                       rounding of the rescoring kernel's fp32 FMA prefilter
 //   margin = 2 * (E_pre + E_ref) * 1.01         (E_ref, E_pre doubled for g = 32)
-template <int G, int KPAD>
+template <int G, int KPAD, bool SPLIT>
 __device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G], const float (&ls)[G],
                                          const float *__restrict__ meta, float beta, float w_max, bool valid,
                                          __half *__restrict__ a_row, float *__restrict__ w_out,
                                          float *__restrict__ margin_out, SegHdr *__restrict__ seg_row,
-                                         uint32_t *__restrict__ rec_row, int nseg)
+                                         uint32_t *__restrict__ rec_row, int nseg, uint32_t *__restrict__ wide_dev)
 {
     // segments no CTA will touch must read as empty: (runmax, cnt) = (-inf, 0), no records
     if (valid) {
@@ -244,6 +244,7 @@ __device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G
     }
     if (!(maxA > 0.f) || !isfinite(maxA) || !isfinite(R) || !isfinite(bnorm2)) bad = true;
     float scale = 1.f, w_scaled = -1.f, margin = 0.f;
+    bool wide = false;
     if (!bad) {
         int ex;
         frexpf(maxA, &ex);               // maxA = f * 2^ex, f in [0.5, 1)
@@ -256,19 +257,30 @@ __device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G
         // core's fp32 accumulation of up to 32 products, bounded by 2^-18 P (32 truncating adds of 2^-23
         // relative each; measured worst case on B200 is 25x below the resulting window: scripts/tc_diag.py
         // dump_g4 reports max |error| / (W/2) = 0.02 with the 2^-17 variant of this bound).
-        const float e_round = gq_split_image(G) ? 1.01f * (ldexpf(P, -18) + ldexpf(P, -20)) : 1.01f * ldexpf(P, -10);
-        const float e_floor = ldexpf(sumB / scale + sumA, gq_split_image(G) ? -24 : -25);   // fp16 subnormal floors (hi and lo parts)
+        const float e_round = SPLIT ? 1.01f * (ldexpf(P, -18) + ldexpf(P, -20)) : 1.01f * ldexpf(P, -10);
+        const float e_floor = ldexpf(sumB / scale + sumA, SPLIT ? -24 : -25);   // fp16 subnormal floors (hi and lo parts)
         const float e_tc = e_round + e_floor + ldexpf(eA, -22);
         constexpr float kE = (G > 16) ? 2.0f : 1.0f;   // deeper fp32 summation trees for g = 32
         const float W = 2.02f * (e_tc + kE * ldexpf(R, -20));
         margin = 2.02f * kE * 4.0f * ldexpf(R, -20);
         if (!(W <= w_max) || !isfinite(W * scale)) bad = true;
         else w_scaled = W * scale * 1.001f;
+        if constexpr (gq_has_robust_image(G)) {
+            // GQ_MODE_AUTO feedback: rows whose PLAIN-image window exceeds the cap (they take the exact scan
+            // in fast mode), counted in either mode with one atomic per warp
+            const float w_plain = 2.02f * (1.01f * ldexpf(P, -10) + ldexpf(sumB / scale + sumA, -25) + ldexpf(eA, -22) + kE * ldexpf(R, -20));
+            wide = !(w_plain <= w_max);
+        }
+    }
+    if constexpr (gq_has_robust_image(G)) {
+        const unsigned act = __activemask();
+        const unsigned mw = __ballot_sync(act, wide);
+        if (mw && (threadIdx.x & 31) == (unsigned)(__ffs(mw) - 1)) atomicAdd(wide_dev, (uint32_t)__popc(mw));
     }
     // fp16 row, 16-byte stores.  Plain image: [A | 0]; split image: [hi(A) | hi(A) | lo(A) | 0].
     auto image_value = [&](int k) -> float {
         if (bad) return 0.f;
-        if (!gq_split_image(G)) return k < 2 * G ? A[k < 2 * G ? k : 0] * scale : 0.f;
+        if (!SPLIT) return k < 2 * G ? A[k < 2 * G ? k : 0] * scale : 0.f;
         const int part = k / (2 * G), j = k % (2 * G);
         if (part >= 3) return 0.f;
         const float v = A[j] * scale;                                   // exact: scale is a power of two
@@ -287,12 +299,13 @@ __device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G
     *margin_out = margin;
 }
 
-template <int G, int KPAD>
+template <int G, int KPAD, bool SPLIT>
 __global__ void __launch_bounds__(128)
 rows_prep_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
                  const float *__restrict__ meta, __half *__restrict__ a_img, float *__restrict__ wrow,
                  float *__restrict__ margin, SegHdr *__restrict__ seg_hdr, uint32_t *__restrict__ rec_cnt, int nseg,
-                 int64_t M, int64_t M_pad, float beta, float w_max, uint32_t *__restrict__ counters, int64_t counter_words)
+                 int64_t M, int64_t M_pad, float beta, float w_max, uint32_t *__restrict__ counters, int64_t counter_words,
+                 uint32_t *__restrict__ wide_dev)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < counter_words) counters[r] = 0u;   // device-side lists / arrival counters of this call (counter_words <= M_pad)
@@ -311,21 +324,22 @@ rows_prep_kernel(const float *__restrict__ mu, const float *__restrict__ std, co
 #pragma unroll
         for (int k = 0; k < G; ++k) { m[k] = 0.f; s[k] = 1.f; ls[k] = 0.f; }
     }
-    prep_row<G, KPAD>(m, s, ls, meta, beta, w_max, valid, a_img + r * KPAD, wrow + r, margin + r,
-                      seg_hdr + r * nseg, rec_cnt + r * nseg, nseg);
+    prep_row<G, KPAD, SPLIT>(m, s, ls, meta, beta, w_max, valid, a_img + r * KPAD, wrow + r, margin + r,
+                      seg_hdr + r * nseg, rec_cnt + r * nseg, nseg, wide_dev);
 }
 
 // ---- 2. the tensor-core search ------------------------------------------------------------------
 template <int KPAD>
 struct TcSmem {
     static constexpr int kBTileBytes = kTileN * KPAD * 2;
+    static constexpr int kStagesL = kBTileBytes <= 16384 ? kMaxStages : 6;   // ring depth that fits 227 KB
     static constexpr int kBOff = 0;
     // row operand of each of the two row blocks, same canonical K-major core-matrix layout as a B tile
     static constexpr int kABytes = kBlockRows * KPAD * 2;
-    static constexpr int kAOff = kBOff + kStages * kBTileBytes;
+    static constexpr int kAOff = kBOff + kStagesL * kBTileBytes;
     static constexpr int kBarOff = kAOff + 2 * kABytes;
     // barriers: full_b[kStages], empty_b[kStages], a_full[2], acc_full[kAccStages], acc_empty[kAccStages]
-    static constexpr int kNumBars = 2 * kStages + 2 + 2 * kAccStages;
+    static constexpr int kNumBars = 2 * kStagesL + 2 + 2 * kAccStages;
     static constexpr int kSlotOff = kBarOff + kNumBars * 8;
     static constexpr int kBytes = kSlotOff + 16;
 };
@@ -419,6 +433,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                    int nseg, float *__restrict__ dump)
 {
     using L = TcSmem<KPAD>;
+    constexpr int kStages = L::kStagesL;
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t smem_base;
     // pin the shared-window base in a register (otherwise it is rematerialised from SR_CgaCtaId
@@ -990,7 +1005,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-template <int G, int KPAD>
+template <int G, int KPAD, bool SPLIT>
 static int run_tc(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
                   int64_t *idx, float *zhat, const TcPlan &p, const TcWorkspace &w, uint32_t *stats,
                   float w_max, cudaStream_t stream, bool do_prep = true)
@@ -1007,9 +1022,9 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
     // between two kernels would break the programmatic launch chain)
     int rc = GQ_OK;
     if (do_prep) {
-        rows_prep_kernel<G, KPAD><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
+        rows_prep_kernel<G, KPAD, SPLIT><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
             mu, std, lstd, cb->meta, w.a_img, w.wrow, w.margin, w.seg, w.rec_cnt, p.nseg, M, p.M_pad, cb->beta, w_max,
-            w.counters, w.counter_bytes / 4);
+            w.counters, w.counter_bytes / 4, cb->wide_dev);
         rc = check_launch("rows_prep_kernel");
         if (rc) return rc;
         count_launch(1);
@@ -1025,8 +1040,8 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
         cudaEventRecord(ev0, stream);
     }
     launch_chained(quantize_tc_kernel<KPAD, false>, dim3(p.ctas), dim3(kThreads), L::kBytes, stream,
-                   w.a_img, cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N, p.tiles, p.total_steps, p.steps_per_cta, p.nseg,
-                   nullptr);
+                   w.a_img, (SPLIT && gq_has_robust_image(G)) ? cb->bimg_robust : cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N,
+                   p.tiles, p.total_steps, p.steps_per_cta, p.nseg, nullptr);
     if (g_prof) {
         cudaEventRecord(ev1, stream);
         g_prof_events.emplace_back(ev0, ev1);
@@ -1058,7 +1073,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
 
 // Debug/diagnostic path (tests only): runs row prep + the search with the DUMP epilogue and
 // returns the raw fp16 tensor-core scores [M_pad, n_pad] plus the scaled windows [M_pad].
-template <int G, int KPAD>
+template <int G, int KPAD, bool SPLIT>
 static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
                        const TcPlan &p, const TcWorkspace &w, float *dump, float *wrow_out, float w_max,
                        cudaStream_t stream)
@@ -1067,13 +1082,13 @@ static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std,
     cudaError_t e = cudaFuncSetAttribute(quantize_tc_kernel<KPAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::kBytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
-    rows_prep_kernel<G, KPAD><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
+    rows_prep_kernel<G, KPAD, SPLIT><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
         mu, std, lstd, cb->meta, w.a_img, w.wrow, w.margin, w.seg, w.rec_cnt, p.nseg, M, p.M_pad, cb->beta, w_max,
-        w.counters, w.counter_bytes / 4);
+        w.counters, w.counter_bytes / 4, cb->wide_dev);
     int rc = check_launch("rows_prep_kernel");
     if (rc) return rc;
     quantize_tc_kernel<KPAD, true><<<p.ctas, kThreads, L::kBytes, stream>>>(
-        w.a_img, cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N, p.tiles, p.total_steps, p.steps_per_cta, p.nseg,
+        w.a_img, (SPLIT && gq_has_robust_image(G)) ? cb->bimg_robust : cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N, p.tiles, p.total_steps, p.steps_per_cta, p.nseg,
         dump);
     rc = check_launch("quantize_tc_kernel<dump>");
     if (rc) return rc;
@@ -1090,14 +1105,14 @@ static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std,
 // Thread <-> (token, sub-codebook j), addressing as in gq_kl.cu.  std = exp(0.5*clamp(logvar)) and
 // log(std) use the same libdevice expf/logf torch's CUDA kernels call; zhat_noquant = mu + eps*std is
 // formed with one multiply and one add (no FMA), as torch's two kernels do.
-template <int G, int KPAD>
+template <int G, int KPAD, bool SPLIT>
 __global__ void __launch_bounds__(128)
 frontend_kernel(const float *__restrict__ z, const float *__restrict__ eps, const float *__restrict__ meta,
                 float *__restrict__ mu_r, float *__restrict__ std_r, float *__restrict__ lstd_r,
                 float *__restrict__ zhat_nq, __half *__restrict__ a_img, float *__restrict__ wrow,
                 float *__restrict__ margin, SegHdr *__restrict__ seg_hdr, uint32_t *__restrict__ rec_cnt, int nseg,
                 int64_t b, int64_t l, int C, int layout, float lv_lo, float lv_hi, int64_t M, int64_t M_pad,
-                float beta, float w_max, uint32_t *__restrict__ counters, int64_t counter_words)
+                float beta, float w_max, uint32_t *__restrict__ counters, int64_t counter_words, uint32_t *__restrict__ wide_dev)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < counter_words) counters[i] = 0u;   // device-side lists / arrival counters of this call (counter_words <= M_pad)
@@ -1151,8 +1166,8 @@ frontend_kernel(const float *__restrict__ z, const float *__restrict__ eps, cons
 #pragma unroll
         for (int k = 0; k < G; ++k) { m[k] = 0.f; s[k] = 1.f; ls[k] = 0.f; }
     }
-    prep_row<G, KPAD>(m, s, ls, meta, beta, w_max, valid, a_img + r * KPAD, wrow + r, margin + r,
-                      seg_hdr + r * nseg, rec_cnt + r * nseg, nseg);
+    prep_row<G, KPAD, SPLIT>(m, s, ls, meta, beta, w_max, valid, a_img + r * KPAD, wrow + r, margin + r,
+                      seg_hdr + r * nseg, rec_cnt + r * nseg, nseg, wide_dev);
 }
 
 // Row indices -> the module's output tensors (gaussian.py:153-158): indices [b,l,ncb] / [b,ncb,h,w]
@@ -1225,7 +1240,19 @@ int64_t latent_workspace_bytes(const gq_codebook *cb, int64_t M)
 
 static float g_w_max = 3.0f;
 
-template <int G, int KPAD>
+// Which operand image a call uses (groups 8 and 16; gq_mode in gq_b200.h).  AUTO reads the feedback the
+// last completed call on this codebook left in pinned host memory -- no synchronisation, so the decision
+// may lag by a call or two, which is fine for a stationary latent distribution.
+static bool use_robust_image(const gq_codebook *cb)
+{
+    if (!cb->kpad_robust) return false;
+    if (cb->mode == GQ_MODE_ROBUST) return true;
+    if (cb->mode == GQ_MODE_FAST || !cb->fb_host) return false;
+    const uint32_t wide = cb->fb_host[0], rows = cb->fb_host[1];
+    return rows > 0 && (uint64_t)wide * 16u > (uint64_t)rows;
+}
+
+template <int G, int KPAD, bool SPLIT>
 static int run_latent(const gq_codebook *cb, const float *z, const float *eps, int64_t b, int64_t l, int C,
                       int layout, float lv_lo, float lv_hi, int64_t *idx_out, float *zhat_out, float *zhat_nq,
                       const LatentWorkspace &lw, uint32_t *stats, cudaStream_t stream)
@@ -1234,12 +1261,12 @@ static int run_latent(const gq_codebook *cb, const float *z, const float *eps, i
     const int64_t M = b * l * ncb;
     TcPlan p = make_plan(cb, M);
     TcWorkspace w = carve(cb, p, lw.tc);
-    frontend_kernel<G, KPAD><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
+    frontend_kernel<G, KPAD, SPLIT><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
         z, eps, cb->meta, lw.mu_r, lw.std_r, lw.lstd_r, zhat_nq, w.a_img, w.wrow, w.margin, w.seg, w.rec_cnt, p.nseg, b, l, C,
-        layout, lv_lo, lv_hi, M, p.M_pad, cb->beta, g_w_max, w.counters, w.counter_bytes / 4);
+        layout, lv_lo, lv_hi, M, p.M_pad, cb->beta, g_w_max, w.counters, w.counter_bytes / 4, cb->wide_dev);
     int rc = check_launch("frontend_kernel");
     if (rc) return rc;
-    rc = run_tc<G, KPAD>(cb, lw.mu_r, lw.std_r, lw.lstd_r, M, lw.idx_rows, nullptr, p, w, stats, g_w_max, stream,
+    rc = run_tc<G, KPAD, SPLIT>(cb, lw.mu_r, lw.std_r, lw.lstd_r, M, lw.idx_rows, nullptr, p, w, stats, g_w_max, stream,
                          /*do_prep=*/false);
     if (rc) return rc;
     int blocks = (int)imin((M + 255) / 256, (int64_t)device_sm_count() * 8);
@@ -1270,14 +1297,15 @@ int launch_quantize_latent(const gq_codebook *cb, const float *z, const float *e
         return GQ_ERR_WORKSPACE;
     }
     if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) { set_error("workspace must be 256-byte aligned"); return GQ_ERR_INVALID; }
-#define GQ_LAT(GG, KK) return run_latent<GG, KK>(cb, z, eps, b, l, C, layout, lv_lo, lv_hi, idx_out, zhat_out, zhat_nq, lw, stats, stream)
+#define GQ_LAT(GG, KK, SS) return run_latent<GG, KK, SS>(cb, z, eps, b, l, C, layout, lv_lo, lv_hi, idx_out, zhat_out, zhat_nq, lw, stats, stream)
+    const bool robust = use_robust_image(cb);
     switch (cb->g) {
-    case 1: GQ_LAT(1, 16);
-    case 2: GQ_LAT(2, 16);
-    case 4: GQ_LAT(4, 32);
-    case 8: GQ_LAT(8, 16);
-    case 16: GQ_LAT(16, 32);
-    case 32: GQ_LAT(32, 64);
+    case 1: GQ_LAT(1, 16, true);
+    case 2: GQ_LAT(2, 16, true);
+    case 4: GQ_LAT(4, 32, true);
+    case 8: if (robust) GQ_LAT(8, 48, true); else GQ_LAT(8, 16, false);
+    case 16: if (robust) GQ_LAT(16, 96, true); else GQ_LAT(16, 32, false);
+    case 32: GQ_LAT(32, 64, false);
     default: set_error("group %d unsupported", cb->g); return GQ_ERR_INVALID;
     }
 #undef GQ_LAT
@@ -1306,13 +1334,18 @@ int launch_quantize_tc(const gq_codebook *cb, const float *mu, const float *std,
         return GQ_ERR_WORKSPACE;
     }
     if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) { set_error("workspace must be 256-byte aligned"); return GQ_ERR_INVALID; }
+    const bool robust = use_robust_image(cb);
     switch (cb->g) {
-    case 1: return run_tc<1, 16>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
-    case 2: return run_tc<2, 16>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
-    case 4: return run_tc<4, 32>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
-    case 8: return run_tc<8, 16>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
-    case 16: return run_tc<16, 32>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
-    case 32: return run_tc<32, 64>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
+    case 1: return run_tc<1, 16, true>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
+    case 2: return run_tc<2, 16, true>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
+    case 4: return run_tc<4, 32, true>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
+    case 8:
+        if (robust) return run_tc<8, 48, true>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
+        return run_tc<8, 16, false>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
+    case 16:
+        if (robust) return run_tc<16, 96, true>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
+        return run_tc<16, 32, false>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
+    case 32: return run_tc<32, 64, false>(cb, mu, std, lstd, M, idx, zhat, p, w, stats, g_w_max, stream);
     default: set_error("group %d unsupported", cb->g); return GQ_ERR_INVALID;
     }
 }
@@ -1325,9 +1358,11 @@ int debug_tc_scores(const gq_codebook *cb, const float *mu, const float *std, co
     TcWorkspace w = carve(cb, p, ws);
     if (ws == nullptr || ws_bytes < w.bytes) { set_error("workspace too small"); return GQ_ERR_WORKSPACE; }
     switch (cb->g) {
-    case 4: return run_tc_dump<4, 32>(cb, mu, std, lstd, M, p, w, dump, wrow_out, g_w_max, stream);
-    case 8: return run_tc_dump<8, 16>(cb, mu, std, lstd, M, p, w, dump, wrow_out, g_w_max, stream);
-    case 16: return run_tc_dump<16, 32>(cb, mu, std, lstd, M, p, w, dump, wrow_out, g_w_max, stream);
+    case 4: return run_tc_dump<4, 32, true>(cb, mu, std, lstd, M, p, w, dump, wrow_out, g_w_max, stream);
+    case 8: return run_tc_dump<8, 16, false>(cb, mu, std, lstd, M, p, w, dump, wrow_out, g_w_max, stream);
+    case 16:
+        if (cb->mode == GQ_MODE_ROBUST) return run_tc_dump<16, 96, true>(cb, mu, std, lstd, M, p, w, dump, wrow_out, g_w_max, stream);
+        return run_tc_dump<16, 32, false>(cb, mu, std, lstd, M, p, w, dump, wrow_out, g_w_max, stream);
     default: set_error("debug dump supports g in {4,8,16}"); return GQ_ERR_INVALID;
     }
 }

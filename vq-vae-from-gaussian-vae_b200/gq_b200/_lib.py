@@ -18,6 +18,7 @@ LIB_PATH = Path(os.environ.get("GQ_B200_LIB") or (Path(__file__).resolve().paren
 GQ_OK = 0
 GQ_LAYOUT_BLC = 0
 GQ_LAYOUT_BCHW = 1
+GQ_MODE_AUTO, GQ_MODE_FAST, GQ_MODE_ROBUST = 0, 1, 2
 ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/gq_b200.h one to one
@@ -30,6 +31,7 @@ PROTOTYPES = {
     "gq_codebook_create": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p,
                                    POINTER(c_void_p)]),
     "gq_codebook_destroy": (None, [c_void_p]),
+    "gq_codebook_set_mode": (c_int, [c_void_p, c_int]),
     "gq_codebook_size": (c_int64, [c_void_p]),
     "gq_codebook_group": (c_int, [c_void_p]),
     "gq_codebook_data": (c_void_p, [c_void_p]),

@@ -96,6 +96,15 @@ class Codebook:
             raise RuntimeError("codebook handle was destroyed")
         return self._handle
 
+    def set_mode(self, mode: str) -> None:
+        """Search precision for groups 8 and 16 (gq_mode in gq_b200.h): "auto" (default: fast until many
+        rows of a call had a too-wide fp16 window, then robust), "fast" (fp16 image, wide rows take the
+        exact scan) or "robust" (split-precision image, ~1.4x the search time)."""
+        modes = {"auto": _lib.GQ_MODE_AUTO, "fast": _lib.GQ_MODE_FAST, "robust": _lib.GQ_MODE_ROBUST}
+        if mode not in modes:
+            raise ValueError(f"mode must be one of {sorted(modes)}")
+        check(_lib.lib().gq_codebook_set_mode(self.handle, modes[mode]), "gq_codebook_set_mode")
+
     def workspace(self, M: int) -> torch.Tensor:
         need = int(_lib.lib().gq_quantize_workspace_bytes(self.handle, M))
         return self._grow(need)

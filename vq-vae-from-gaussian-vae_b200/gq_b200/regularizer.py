@@ -66,7 +66,15 @@ class _GQBase(nn.Module):
         if self._cb is None or self._cb_key != key:
             self._cb = Codebook(ps, self.normal_log_prob, float(self.beta))
             self._cb_key = key
+            self._cb.set_mode(getattr(self, "_search_mode", "auto"))
         return self._cb
+
+    def set_search_mode(self, mode: str) -> None:
+        """Not in the reference module: search precision for groups 8 / 16 ("auto", "fast", "robust";
+        Codebook.set_mode).  Results are identical in every mode; only the speed on low-variance rows differs."""
+        self._search_mode = mode
+        if getattr(self, "_cb", None) is not None:
+            self._cb.set_mode(mode)
 
 
 class GaussianQuantRegularizer(_GQBase):
