@@ -64,14 +64,16 @@ def test_quantize_rows_golden(gq, name, exact):
     assert np.array_equal(zhat.cpu().numpy(), o_zhat)        # bit-exact codewords
 
 
+@pytest.mark.parametrize("mode", ["auto", "robust"])
 @pytest.mark.parametrize("name", EVAL_CASES)
-def test_module_eval_golden(gq, name):
+def test_module_eval_golden(gq, name, mode):
     """Drop-in module: z -> (zhat, indices) must equal the reference's outputs.  exp/log run in
     torch on the GPU here and on the CPU in the fixture, so rows whose std differs by an ulp
     could move a near-tie; count mismatches and require every one to be a near-tie."""
     g = load_golden(name)
     reg = gq.GaussianQuantRegularizer(format=str(g["format"]), n_samples=int(g["n_samples"]), group=int(g["group"]),
                                       beta=float(g["beta"]), backend="cuda").cuda().eval()
+    reg.set_search_mode(mode)      # groups 8 / 16: fp16 or split-precision operand image; same results
     cb_np, _ = golden_codebook(g)
     assert np.array_equal(reg.prior_samples.cpu().numpy(), cb_np)
     zhat, info = reg(dev(g["z"]))
