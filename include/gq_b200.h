@@ -167,7 +167,7 @@ int gq_kl_bwd(const float *z, const float *eps, const float *w, const float *gra
 /* ---- measurement and diagnostics (no reference counterpart) ------------------------------
  * gq_profile_enable(n): every n-th later gq_quantize (n = 1: every one; 0: off) records a CUDA-event pair around its search
  * kernel on the caller's stream; gq_profile_read sums and clears them (synchronises on the
- * recorded events).  gq_set_window_max: rows whose rigorous error window exceeds `w` (score
+ * recorded events).  gq_set_window_max: rows whose rigorous error window exceeds `w` (32 `w` with the split-precision image; score
  * units) go to the exact scan (default 3.0).  gq_debug_tc_scores dumps the raw tensor-core
  * score matrix [M_pad, n_pad] and the scaled per-row windows [M_pad]; gq_debug_plan returns
  * the stream-K decomposition {units, tiles, ctas, steps_per_cta, nseg, M_pad}. */
