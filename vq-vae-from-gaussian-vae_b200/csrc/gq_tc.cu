@@ -1271,12 +1271,19 @@ static int run_latent(const gq_codebook *cb, const float *z, const float *eps, i
         layout, lv_lo, lv_hi, M, p.M_pad, cb->beta, g_w_max, w.counters, w.counter_bytes / 4, cb->wide_dev);
     int rc = check_launch("frontend_kernel");
     if (rc) return rc;
+    count_launch(1);
+    if (layout == GQ_LAYOUT_BLC && ncb == 1) {
+        // rows are tokens and a row's codeword is the token's channel vector: the rescoring kernels write
+        // the final tensors themselves, no permute / gather pass is needed
+        return run_tc<G, KPAD, SPLIT>(cb, lw.mu_r, lw.std_r, lw.lstd_r, M, idx_out, zhat_out, p, w, stats, g_w_max, stream,
+                                      /*do_prep=*/false);
+    }
     rc = run_tc<G, KPAD, SPLIT>(cb, lw.mu_r, lw.std_r, lw.lstd_r, M, lw.idx_rows, nullptr, p, w, stats, g_w_max, stream,
                          /*do_prep=*/false);
     if (rc) return rc;
     int blocks = (int)imin((M + 255) / 256, (int64_t)device_sm_count() * 8);
     launch_chained(finalize_kernel<G>, dim3(blocks), dim3(256), 0, stream, lw.idx_rows, cb->cb, idx_out, zhat_out, b, l, ncb, layout);
-    count_launch(2);
+    count_launch(1);
     return check_launch("finalize_kernel");
 }
 
