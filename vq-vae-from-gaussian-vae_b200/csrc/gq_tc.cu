@@ -214,12 +214,13 @@ __device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G
                                          float *__restrict__ margin_out, SegHdr *__restrict__ seg_row,
                                          uint32_t *__restrict__ rec_row, int nseg, uint32_t *__restrict__ wide_dev)
 {
-    // segments no CTA will touch must read as empty: (runmax, cnt) = (-inf, 0), no records
+    // Segments no CTA will touch must read as empty.  Only the compact record counters are cleared
+    // (nseg contiguous words per row); a summary whose counter is zero is stale memory from an earlier
+    // call and is ignored by the readers -- clearing the 64-byte summaries themselves cost a partial
+    // sector write per segment, a third of this kernel's traffic.
+    (void)seg_row;
     if (valid) {
-        for (int sgi = 0; sgi < nseg; ++sgi) {
-            *reinterpret_cast<uint2 *>(&seg_row[sgi]) = make_uint2(0xff800000u, 0u);
-            rec_row[sgi] = 0u;
-        }
+        for (int sgi = 0; sgi < nseg; ++sgi) rec_row[sgi] = 0u;
     }
     float A[2 * G];
     bool bad = !valid;
@@ -851,25 +852,32 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
     }
 }
 
-struct RowIn { float w, margin, pm, ps, pl; uint4 q; };
+struct RowIn { float w, margin, pm, ps; uint4 q; };
 
 template <int G>
 __device__ __forceinline__ RowIn fetch_row(int64_t r, int lane, const float *__restrict__ wrow,
                                            const float *__restrict__ margin_row, const SegHdr *__restrict__ seg_hdr,
                                            const float *__restrict__ mu, const float *__restrict__ std,
-                                           const float *__restrict__ lstd, int nseg)
+                                           const uint32_t *__restrict__ rec_cnt, int nseg)
 {
     RowIn in;
     const int seg_l = lane >> 2, quarter = lane & 3;
     in.w = __ldg(wrow + r);
     in.margin = __ldg(margin_row + r);
     in.q = make_uint4(0xff800000u, 0u, 0xff800000u, 0u);
-    if (seg_l < nseg) in.q = __ldg(reinterpret_cast<const uint4 *>(seg_hdr + r * nseg + seg_l) + quarter);
-    in.pm = in.ps = in.pl = 0.f;
+    // a summary counts only if its segment recorded something in THIS call (the prep kernel clears the
+    // counters, not the summaries): both loads are issued together, the select happens at the use
+    uint32_t recs = 0u;
+    uint4 q = in.q;
+    if (seg_l < nseg) {
+        recs = __ldg(rec_cnt + r * nseg + seg_l);
+        q = __ldg(reinterpret_cast<const uint4 *>(seg_hdr + r * nseg + seg_l) + quarter);
+    }
+    if (recs != 0u) in.q = q;
+    in.pm = in.ps = 0.f;
     if (lane < G) {
         in.pm = __ldg(mu + r * G + lane);
         in.ps = __ldg(std + r * G + lane);
-        if (lstd) in.pl = __ldg(lstd + r * G + lane);
     }
     return in;
 }
@@ -918,11 +926,11 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
         }
     } else {
         RowIn cur{}, nxt{};
-        if (warp_global < M) cur = fetch_row<G>(warp_global, lane, wrow, margin_row, seg_hdr, mu, std, lstd, nseg);
+        if (warp_global < M) cur = fetch_row<G>(warp_global, lane, wrow, margin_row, seg_hdr, mu, std, rec_cnt, nseg);
         for (int64_t r = warp_global; r < M; r += nwarps) {
             const bool has_next = r + nwarps < M;
             if (has_next)   // in flight while this row is processed
-                nxt = fetch_row<G>(r + nwarps, lane, wrow, margin_row, seg_hdr, mu, std, lstd, nseg);
+                nxt = fetch_row<G>(r + nwarps, lane, wrow, margin_row, seg_hdr, mu, std, rec_cnt, nseg);
 
             int verdict = 0;   // 0 = decided here, 1 = settle (summaries), 2 = settle (full lists), 3 = exact scan
             int best_idx = 0;
@@ -1113,7 +1121,7 @@ static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std,
 template <int G, int KPAD, bool SPLIT>
 __global__ void __launch_bounds__(128)
 frontend_kernel(const float *__restrict__ z, const float *__restrict__ eps, const float *__restrict__ meta,
-                float *__restrict__ mu_r, float *__restrict__ std_r, float *__restrict__ lstd_r,
+                float *__restrict__ mu_r, float *__restrict__ std_r,
                 float *__restrict__ zhat_nq, __half *__restrict__ a_img, float *__restrict__ wrow,
                 float *__restrict__ margin, SegHdr *__restrict__ seg_hdr, uint32_t *__restrict__ rec_cnt, int nseg,
                 int64_t b, int64_t l, int C, int layout, float lv_lo, float lv_hi, int64_t M, int64_t M_pad,
@@ -1161,11 +1169,10 @@ frontend_kernel(const float *__restrict__ z, const float *__restrict__ eps, cons
             for (int k = 0; k < G / 4; ++k) {
                 reinterpret_cast<float4 *>(mu_r + r * G)[k] = make_float4(m[4 * k], m[4 * k + 1], m[4 * k + 2], m[4 * k + 3]);
                 reinterpret_cast<float4 *>(std_r + r * G)[k] = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
-                reinterpret_cast<float4 *>(lstd_r + r * G)[k] = make_float4(ls[4 * k], ls[4 * k + 1], ls[4 * k + 2], ls[4 * k + 3]);
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < G; ++k) { mu_r[r * G + k] = m[k]; std_r[r * G + k] = s[k]; lstd_r[r * G + k] = ls[k]; }
+            for (int k = 0; k < G; ++k) { mu_r[r * G + k] = m[k]; std_r[r * G + k] = s[k]; }
         }
     } else {
 #pragma unroll
@@ -1267,7 +1274,7 @@ static int run_latent(const gq_codebook *cb, const float *z, const float *eps, i
     TcPlan p = make_plan(cb, M);
     TcWorkspace w = carve(cb, p, lw.tc);
     frontend_kernel<G, KPAD, SPLIT><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
-        z, eps, cb->meta, lw.mu_r, lw.std_r, lw.lstd_r, zhat_nq, w.a_img, w.wrow, w.margin, w.seg, w.rec_cnt, p.nseg, b, l, C,
+        z, eps, cb->meta, lw.mu_r, lw.std_r, zhat_nq, w.a_img, w.wrow, w.margin, w.seg, w.rec_cnt, p.nseg, b, l, C,
         layout, lv_lo, lv_hi, M, p.M_pad, cb->beta, g_w_max, w.counters, w.counter_bytes / 4, cb->wide_dev);
     int rc = check_launch("frontend_kernel");
     if (rc) return rc;
@@ -1275,10 +1282,12 @@ static int run_latent(const gq_codebook *cb, const float *z, const float *eps, i
     if (layout == GQ_LAYOUT_BLC && ncb == 1) {
         // rows are tokens and a row's codeword is the token's channel vector: the rescoring kernels write
         // the final tensors themselves, no permute / gather pass is needed
-        return run_tc<G, KPAD, SPLIT>(cb, lw.mu_r, lw.std_r, lw.lstd_r, M, idx_out, zhat_out, p, w, stats, g_w_max, stream,
+        return run_tc<G, KPAD, SPLIT>(cb, lw.mu_r, lw.std_r, nullptr, M, idx_out, zhat_out, p, w, stats, g_w_max, stream,
                                       /*do_prep=*/false);
     }
-    rc = run_tc<G, KPAD, SPLIT>(cb, lw.mu_r, lw.std_r, lw.lstd_r, M, lw.idx_rows, nullptr, p, w, stats, g_w_max, stream,
+    // (log std is not materialised: the settle / exact kernels take logf(std) with the libdevice function
+    // the front-end and torch use, so the values are the same bits)
+    rc = run_tc<G, KPAD, SPLIT>(cb, lw.mu_r, lw.std_r, nullptr, M, lw.idx_rows, nullptr, p, w, stats, g_w_max, stream,
                          /*do_prep=*/false);
     if (rc) return rc;
     int blocks = (int)imin((M + 255) / 256, (int64_t)device_sm_count() * 8);
