@@ -748,36 +748,44 @@ __device__ __forceinline__ float prefilter_score(const float (&x)[G], const floa
     return a2;
 }
 
-// The same with the row's mu and 1/(2 var) read from shared memory (16-byte broadcast loads) instead of
-// 2 G registers: identical operation order, hence identical values; lets four blocks share an SM.
+// The same with the row's parameters read from shared memory (16-byte broadcast loads) instead of 2 G
+// registers, and -- for G % 4 == 0 -- on packed fp32 pairs (FADD2 / FMUL2 / FFMA2: half the issue slots;
+// this kernel is issue bound).  `nm` holds -mu and `nri` holds -1/(2 var), so that x + nm = x - mu and
+// fma(d*d, nri, a) = fma(-d*d, ri, a) exactly.  Even and odd dimensions accumulate separately and are
+// added at the end: a different rounding sequence than the scalar form above, with shorter chains, so the
+// same 3 * 2^-20 * R bound covers it; the value is only ever compared with other values of this function.
 template <int G>
-__device__ __forceinline__ float prefilter_score_smem(const float (&x)[G], const float *__restrict__ m,
-                                                      const float *__restrict__ ri, float hb)
+__device__ __forceinline__ float prefilter_score_smem(const float (&x)[G], const float *__restrict__ nm,
+                                                      const float *__restrict__ nri, float hb)
 {
-    float a2 = 0.f;
     if constexpr (G % 4 == 0) {
+        float2 acc = make_float2(0.f, 0.f);
+        const float2 hb2 = make_float2(hb, hb);
 #pragma unroll
         for (int k4 = 0; k4 < G / 4; ++k4) {
-            const float4 mm = reinterpret_cast<const float4 *>(m)[k4];
-            const float4 rr = reinterpret_cast<const float4 *>(ri)[k4];
-            const float mv[4] = {mm.x, mm.y, mm.z, mm.w}, rv[4] = {rr.x, rr.y, rr.z, rr.w};
+            const float4 mm = reinterpret_cast<const float4 *>(nm)[k4];
+            const float4 rr = reinterpret_cast<const float4 *>(nri)[k4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float xv = x[4 * k4 + j];
-                const float d = xv - mv[j];
-                a2 = fmaf(-d * d, rv[j], a2);
-                a2 = fmaf(hb * xv, xv, a2);
+            for (int j = 0; j < 2; ++j) {
+                const float2 xv = make_float2(x[4 * k4 + 2 * j], x[4 * k4 + 2 * j + 1]);
+                const float2 mv = j ? make_float2(mm.z, mm.w) : make_float2(mm.x, mm.y);
+                const float2 rv = j ? make_float2(rr.z, rr.w) : make_float2(rr.x, rr.y);
+                const float2 d = __fadd2_rn(xv, mv);
+                acc = __ffma2_rn(__fmul2_rn(d, d), rv, acc);
+                acc = __ffma2_rn(__fmul2_rn(hb2, xv), xv, acc);
             }
         }
+        return acc.x + acc.y;
     } else {
+        float a2 = 0.f;
 #pragma unroll
         for (int k = 0; k < G; ++k) {
-            const float d = x[k] - m[k];
-            a2 = fmaf(-d * d, ri[k], a2);
+            const float d = x[k] + nm[k];
+            a2 = fmaf(d * d, nri[k], a2);
             a2 = fmaf(hb * x[k], x[k], a2);
         }
+        return a2;
     }
-    return a2;
 }
 
 constexpr int kMaxChunks = 64;   // surviving chunks one row may carry into the rescoring (else: exact scan)
@@ -898,7 +906,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                uint32_t *__restrict__ settle_count, const uint32_t *__restrict__ rec_cnt,
                unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats)
 {
-    __shared__ __align__(16) float s_par[kRescoreWarps][2][G < 4 ? 4 : G];   // mu, 1/den of the warp's row
+    __shared__ __align__(16) float s_par[kRescoreWarps][2][G < 4 ? 4 : G];   // -mu, -1/den of the warp's row
     __shared__ uint32_t s_chunks[kRescoreWarps][kMaxChunks];
     pdl_wait();
     const int lane = threadIdx.x & 31;
@@ -962,8 +970,8 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                 if (ok_b) s_chunks[wib][na + __popc(mb & lt)] = q.w;
                 if (lane < G) {
                     const float dn = __fmul_rn(2.0f, __fmul_rn(cur.ps, cur.ps));
-                    s_par[wib][0][lane] = cur.pm;
-                    s_par[wib][1][lane] = 1.0f / dn;
+                    s_par[wib][0][lane] = -cur.pm;          // negated: see prefilter_score_smem
+                    s_par[wib][1][lane] = -(1.0f / dn);
                 }
                 __syncwarp();
                 if (nchunks == 0) verdict = 3;
