@@ -146,6 +146,7 @@ struct TcWorkspace {
     Cand *cand;         // [M_pad, nseg, kCap]
     uint32_t *fb_rows;  // [M] fallback row list (exact scan)
     uint32_t *st_rows;  // [M] rows whose prefilter left several contenders (settle_kernel); bit 31: use the full record list
+    uint32_t *st_chunks; // [M][8] per listed row: {number of surviving chunks (<= 7, else ~0), chunk ids}: saves settle the re-derivation
     uint32_t *rec_cnt;  // [M_pad, nseg] records written per (row, segment) (may exceed kCap: list overflow)
     unsigned long long *fb_keys;  // [M] packed (score, ~index) argmax keys of the sliced exact scan
     uint32_t *counters; // [0] fallback count, [1] settle count, [64..] per-row-group arrival counters of the scan
@@ -174,6 +175,8 @@ static TcWorkspace carve(const gq_codebook *cb, const TcPlan &p, void *base)
     off = align_up(off + p.M * 4, 256);
     w.st_rows = reinterpret_cast<uint32_t *>(ptr + off);
     off = align_up(off + p.M * 4, 256);
+    w.st_chunks = reinterpret_cast<uint32_t *>(ptr + off);
+    off = align_up(off + p.M * 32, 256);
     w.rec_cnt = reinterpret_cast<uint32_t *>(ptr + off);
     off = align_up(off + p.M_pad * p.nseg * 4, 256);
     w.fb_keys = reinterpret_cast<unsigned long long *>(ptr + off);
@@ -799,7 +802,7 @@ __global__ void __launch_bounds__(128)
 settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
               const float *__restrict__ cb, const float *__restrict__ nlpb, const float *__restrict__ wrow,
               const SegHdr *__restrict__ seg_hdr, const Cand *__restrict__ cand, const uint32_t *__restrict__ rec_cnt,
-              const uint32_t *__restrict__ rows, const uint32_t *__restrict__ nrows, int64_t N, int tiles,
+              const uint32_t *__restrict__ rows, const uint32_t *__restrict__ row_chunks, const uint32_t *__restrict__ nrows, int64_t N, int tiles,
               int steps_per_cta, int nseg, int64_t *__restrict__ idx_out, float *__restrict__ zhat_out,
               uint32_t *__restrict__ fb_rows, uint32_t *__restrict__ fb_count, unsigned long long *__restrict__ fb_keys)
 {
@@ -810,11 +813,10 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
         const uint32_t entry = rows[it];
         const bool full = (entry & 0x80000000u) != 0u;   // a segment kept more than kSurv survivors: walk its full list
         const int64_t r = entry & 0x7fffffffu;
-        const uint32_t s0 = (uint32_t)(r / kUnitRows) * (uint32_t)tiles;
-        const int npieces = kHalves * ((int)((s0 + (uint32_t)tiles - 1u) / (uint32_t)steps_per_cta) - (int)(s0 / (uint32_t)steps_per_cta) + 1);
-        float gmax = -CUDART_INF_F;
-        for (int s = 0; s < npieces; ++s) gmax = fmaxf(gmax, seg_hdr[r * nseg + s].runmax);
-        const float thr = gmax - wrow[r];
+        // rescore_kernel attached the row's surviving chunks (lane i holds word i of the 8-word entry):
+        // one load instead of a walk over the segment summaries
+        const uint32_t my_word = lane < 8 ? __ldg(row_chunks + (int64_t)it * 8 + lane) : 0u;
+        const uint32_t n_listed = __shfl_sync(0xffffffffu, my_word, 0);
         float m[G], den[G], ls[G];
         load_row<G>(mu + r * G, m);
         {
@@ -828,20 +830,32 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
         }
         float best = -CUDART_INF_F;
         int best_idx = 0x7fffffff;
-        for (int s = 0; s < npieces; ++s) {
-            const SegHdr *h = &seg_hdr[r * nseg + s];
-            const Cand *list = full ? cand + (r * nseg + s) * (int64_t)kCap : h->surv;
-            const uint32_t cnt = full ? rec_cnt[r * nseg + s] : h->cnt;   // <= kCap resp. <= kSurv by construction
-            for (uint32_t i = 0; i < cnt; ++i) {
-                const Cand c = list[i];
-                if (!(c.score >= thr)) continue;
-                const int64_t n = (int64_t)c.idx * kChunk + lane;
-                if (n < N) {
-                    float x[G], nb[G];
-                    load_row<G>(cb + n * G, x);
-                    load_row<G>(nlpb + n * G, nb);
-                    const float sc = score_exact<G>(x, nb, m, den, ls);
-                    if (sc > best || (sc == best && (int)n < best_idx)) { best = sc; best_idx = (int)n; }
+        auto score_chunk = [&](uint32_t chunk) {
+            const int64_t n = (int64_t)chunk * kChunk + lane;
+            if (n < N) {
+                float x[G], nb[G];
+                load_row<G>(cb + n * G, x);
+                load_row<G>(nlpb + n * G, nb);
+                const float sc = score_exact<G>(x, nb, m, den, ls);
+                if (sc > best || (sc == best && (int)n < best_idx)) { best = sc; best_idx = (int)n; }
+            }
+        };
+        if (!full && n_listed <= 7u) {
+            for (uint32_t c = 0; c < n_listed; ++c) score_chunk(__shfl_sync(0xffffffffu, my_word, (int)c + 1));
+        } else {
+            const uint32_t s0 = (uint32_t)(r / kUnitRows) * (uint32_t)tiles;
+            const int npieces = kHalves * ((int)((s0 + (uint32_t)tiles - 1u) / (uint32_t)steps_per_cta) - (int)(s0 / (uint32_t)steps_per_cta) + 1);
+            float gmax = -CUDART_INF_F;
+            for (int s = 0; s < npieces; ++s) gmax = fmaxf(gmax, seg_hdr[r * nseg + s].runmax);
+            const float thr = gmax - wrow[r];
+            for (int s = 0; s < npieces; ++s) {
+                const SegHdr *h = &seg_hdr[r * nseg + s];
+                const Cand *list = full ? cand + (r * nseg + s) * (int64_t)kCap : h->surv;
+                const uint32_t cnt = full ? rec_cnt[r * nseg + s] : h->cnt;   // <= kCap resp. <= kSurv by construction
+                for (uint32_t i = 0; i < cnt; ++i) {
+                    const Cand c = list[i];
+                    if (!(c.score >= thr)) continue;
+                    score_chunk(c.idx);
                 }
             }
         }
@@ -902,7 +916,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                const float *__restrict__ cb, const float *__restrict__ wrow, const float *__restrict__ margin_row,
                const SegHdr *__restrict__ seg_hdr, int64_t M, int64_t N, int nseg, float beta,
                int64_t *__restrict__ idx_out, float *__restrict__ zhat_out, uint32_t *__restrict__ fb_rows,
-               uint32_t *__restrict__ fb_count, uint32_t *__restrict__ settle_rows,
+               uint32_t *__restrict__ fb_count, uint32_t *__restrict__ settle_rows, uint32_t *__restrict__ settle_chunks,
                uint32_t *__restrict__ settle_count, const uint32_t *__restrict__ rec_cnt,
                unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats)
 {
@@ -942,6 +956,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
 
             int verdict = 0;   // 0 = decided here, 1 = settle (summaries), 2 = settle (full lists), 3 = exact scan
             int best_idx = 0;
+            int n_chunks_row = 0;
             const uint4 q = cur.q;
             float gmax = head ? __uint_as_float(q.x) : -CUDART_INF_F;
 #pragma unroll
@@ -966,6 +981,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                 const unsigned mb = __ballot_sync(0xffffffffu, ok_b);
                 const int na = __popc(ma);
                 const int nchunks = na + __popc(mb);
+                n_chunks_row = nchunks;
                 if (ok_a) s_chunks[wib][__popc(ma & lt)] = id_a;               // <= 8*7 = 56 < kMaxChunks
                 if (ok_b) s_chunks[wib][na + __popc(mb & lt)] = q.w;
                 if (lane < G) {
@@ -1005,9 +1021,23 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
             if (verdict == 0) {
                 if (lane == 0) idx_out[r] = (int64_t)best_idx;
                 if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
-            } else if (lane == 0) {
-                if (verdict == 3) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
-                else settle_rows[atomicAdd(settle_count, 1u)] = (uint32_t)r | (verdict == 2 ? 0x80000000u : 0u);
+            } else if (verdict == 3) {
+                if (lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
+            } else {
+                // hand the row to settle_kernel together with the chunk list just built (lanes 1..7), so
+                // that it need not walk the segment summaries again (a chain of dependent loads)
+                uint32_t slot = 0;
+                if (lane == 0) {
+                    slot = atomicAdd(settle_count, 1u);
+                    settle_rows[slot] = (uint32_t)r | (verdict == 2 ? 0x80000000u : 0u);
+                }
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (lane < 8) {
+                    const bool listed = verdict == 1 && n_chunks_row <= 7;
+                    uint32_t v = listed ? (uint32_t)n_chunks_row : 0xffffffffu;
+                    if (lane > 0) v = (listed && lane - 1 < n_chunks_row) ? s_chunks[wib][lane - 1] : 0u;
+                    settle_chunks[(int64_t)slot * 8 + lane] = v;
+                }
             }
             st_rows += 1;
             st_exact += verdict == 1 ? 1u : 0u;
@@ -1075,12 +1105,12 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
         int blocks = (int)imin(need, (int64_t)device_sm_count() * 8);
         launch_chained(rescore_kernel<G>, dim3(blocks), dim3(kRescoreWarps * 32), 0, stream,
                        mu, std, lstd, cb->cb, w.wrow, w.margin, w.seg, M, cb->N, p.nseg, cb->beta, idx, zhat, w.fb_rows,
-                       w.counters, w.st_rows, w.counters + 1, w.rec_cnt, w.fb_keys, stats);
+                       w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats);
         rc = check_launch("rescore_kernel");
         if (rc) return rc;
         int sblocks = (int)imin((M + 3) / 4, (int64_t)device_sm_count() * 8);
         launch_chained(settle_kernel<G>, dim3(sblocks), dim3(128), 0, stream, mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.seg,
-                       w.cand, w.rec_cnt, w.st_rows, w.counters + 1, cb->N, p.tiles, p.steps_per_cta, p.nseg, idx, zhat,
+                       w.cand, w.rec_cnt, w.st_rows, w.st_chunks, w.counters + 1, cb->N, p.tiles, p.steps_per_cta, p.nseg, idx, zhat,
                        w.fb_rows, w.counters, w.fb_keys);
     }
     rc = check_launch("settle_kernel");
