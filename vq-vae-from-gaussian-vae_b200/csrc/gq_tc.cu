@@ -737,26 +737,13 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 // ---- 3. re-scoring of the recorded chunks: one warp per row, lane = codeword ----------------------
 constexpr int kRescoreWarps = 8;
 
-template <int G>
-__device__ __forceinline__ float prefilter_score(const float (&x)[G], const float (&m)[G], const float (&ri)[G],
-                                                 float hb)
-{
-    float a2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < G; ++k) {
-        const float d = x[k] - m[k];
-        a2 = fmaf(-d * d, ri[k], a2);
-        a2 = fmaf(hb * x[k], x[k], a2);
-    }
-    return a2;
-}
-
-// The same with the row's parameters read from shared memory (16-byte broadcast loads) instead of 2 G
-// registers, and -- for G % 4 == 0 -- on packed fp32 pairs (FADD2 / FMUL2 / FFMA2: half the issue slots;
+// fp32 FMA form of the score (up to a per-row constant), the rescoring prefilter.  The row's parameters
+// are read from shared memory (16-byte broadcast loads) instead of 2 G registers, and -- for G % 4 == 0 --
+// the arithmetic runs on packed fp32 pairs (FADD2 / FMUL2 / FFMA2: half the issue slots;
 // this kernel is issue bound).  `nm` holds -mu and `nri` holds -1/(2 var), so that x + nm = x - mu and
 // fma(d*d, nri, a) = fma(-d*d, ri, a) exactly.  Even and odd dimensions accumulate separately and are
-// added at the end: a different rounding sequence than the scalar form above, with shorter chains, so the
-// same 3 * 2^-20 * R bound covers it; the value is only ever compared with other values of this function.
+// added at the end: <= 6 roundings per term and <= G + 1 per summation path, i.e. <= 1.4 * 2^-20 * R, inside
+// the 3 * 2^-20 * R that prep_row budgets; the value is only ever compared with other values of this function.
 template <int G>
 __device__ __forceinline__ float prefilter_score_smem(const float (&x)[G], const float *__restrict__ nm,
                                                       const float *__restrict__ nri, float hb)
