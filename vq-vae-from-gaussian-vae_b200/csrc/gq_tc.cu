@@ -830,19 +830,29 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
         if (!full && n_listed <= 7u) {
             for (uint32_t c = 0; c < n_listed; ++c) score_chunk(__shfl_sync(0xffffffffu, my_word, (int)c + 1));
         } else {
+            // Walk the summaries (or, for rows flagged `full`, the complete record lists) with the warp in
+            // parallel: lane s takes segment s for the running maxima, lane i takes record i of a list
+            // (kCap = 32 = one record per lane, one coalesced load per segment); the survivors' chunk ids
+            // are then broadcast one by one.  A single lane walking the lists cost 15 us per launch.
             const uint32_t s0 = (uint32_t)(r / kUnitRows) * (uint32_t)tiles;
             const int npieces = kHalves * ((int)((s0 + (uint32_t)tiles - 1u) / (uint32_t)steps_per_cta) - (int)(s0 / (uint32_t)steps_per_cta) + 1);
             float gmax = -CUDART_INF_F;
-            for (int s = 0; s < npieces; ++s) gmax = fmaxf(gmax, seg_hdr[r * nseg + s].runmax);
+            for (int s = lane; s < npieces; s += 32) gmax = fmaxf(gmax, seg_hdr[r * nseg + s].runmax);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
             const float thr = gmax - wrow[r];
+            static_assert(kCap == 32, "one record per lane");
             for (int s = 0; s < npieces; ++s) {
                 const SegHdr *h = &seg_hdr[r * nseg + s];
                 const Cand *list = full ? cand + (r * nseg + s) * (int64_t)kCap : h->surv;
                 const uint32_t cnt = full ? rec_cnt[r * nseg + s] : h->cnt;   // <= kCap resp. <= kSurv by construction
-                for (uint32_t i = 0; i < cnt; ++i) {
-                    const Cand c = list[i];
-                    if (!(c.score >= thr)) continue;
-                    score_chunk(c.idx);
+                Cand c{-CUDART_INF_F, 0u};
+                if ((uint32_t)lane < cnt) c = list[lane];
+                unsigned mask = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && c.score >= thr);
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    score_chunk(__shfl_sync(0xffffffffu, c.idx, src));
                 }
             }
         }
