@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Small end-to-end pass over every kernel of the library (fast / robust search at g = 4, 8, 16, the
+latent path, dequant from the packed stream, usage histogram, KL penalty), meant to be run under
+compute-sanitizer:
+
+    compute-sanitizer --tool memcheck  python scripts/sanitize_smoke.py
+    compute-sanitizer --tool racecheck python scripts/sanitize_smoke.py
+    compute-sanitizer --tool synccheck python scripts/sanitize_smoke.py
+
+Round 1 on B200: 0 errors / 0 hazards with all three tools; indices equal to the oracle's."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "vq-vae-from-gaussian-vae_b200")); sys.path.insert(0, ROOT)
+import numpy as np, torch, gq_b200, oracle
+from gq_b200_host import host_codebook
+dev=torch.device("cuda:0")
+for (N,g,M) in ((1000,16,300),(4096,4,700),(4096,8,300)):
+    cbn,nlp=host_codebook(N,g)
+    cb=gq_b200.Codebook(torch.from_numpy(cbn).to(dev), torch.from_numpy(nlp).to(dev), 1.0)
+    gen=torch.Generator().manual_seed(1)
+    mu=torch.randn(M,g,generator=gen)*0.8; std=torch.exp(0.5*(-1.2+0.4*torch.randn(M,g,generator=gen)))
+    idx,zh=gq_b200.quantize_rows(cb, mu.to(dev), std.to(dev), std.log().to(dev))
+    o,_,_,_=oracle.quantize(mu.numpy(),std.numpy(),std.log().numpy(),cbn,nlp)
+    print(N,g,M,"mismatch",int((idx.cpu().numpy()!=o).sum()))
+    cb.set_mode("robust")
+    idx,zh=gq_b200.quantize_rows(cb, mu.to(dev), std.to(dev), std.log().to(dev))
+    print(" robust mismatch",int((idx.cpu().numpy()!=o).sum()))
+# latent path + KL + tokens
+reg=gq_b200.GaussianQuantRegularizer(format="bchw", n_samples=4096, group=16, backend="cuda").cuda().eval()
+z=torch.randn(2,32,8,8,device=dev)*0.5
+zhat,info=reg(z)
+p=reg.pack_indices(info["indices"]); h=reg.accumulate_usage(info["indices"]); print(reg.codebook_usage(h)[0].item(), torch.equal(reg.dequant(p), zhat))
+reg.train(); zhat,info=reg(z); print(float(info["kl_loss"]))
+torch.cuda.synchronize(); print("done")
