@@ -842,17 +842,32 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
             for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
             const float thr = gmax - wrow[r];
             static_assert(kCap == 32, "one record per lane");
-            for (int s = 0; s < npieces; ++s) {
-                const SegHdr *h = &seg_hdr[r * nseg + s];
-                const Cand *list = full ? cand + (r * nseg + s) * (int64_t)kCap : h->surv;
-                const uint32_t cnt = full ? rec_cnt[r * nseg + s] : h->cnt;   // <= kCap resp. <= kSurv by construction
-                Cand c{-CUDART_INF_F, 0u};
-                if ((uint32_t)lane < cnt) c = list[lane];
-                unsigned mask = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && c.score >= thr);
-                while (mask) {
-                    const int src = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    score_chunk(__shfl_sync(0xffffffffu, c.idx, src));
+            // eight segments per trip, their (independent) loads issued before any is consumed: with many
+            // segments per row (small M: a unit is spread over up to 148 CTAs) this walk is the whole kernel
+            constexpr int kU = 8;
+            for (int sb = 0; sb < npieces; sb += kU) {
+                Cand c[kU];
+                uint32_t cnt[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int s = sb + u;
+                    c[u] = Cand{-CUDART_INF_F, 0u};
+                    cnt[u] = 0u;
+                    if (s < npieces) {
+                        const SegHdr *h = &seg_hdr[r * nseg + s];
+                        const Cand *list = full ? cand + (r * nseg + s) * (int64_t)kCap : h->surv;
+                        cnt[u] = full ? rec_cnt[r * nseg + s] : h->cnt;   // <= kCap resp. <= kSurv by construction
+                        if (lane < (full ? kCap : kSurv)) c[u] = list[lane];   // in bounds; masked by cnt below
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    unsigned mask = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt[u] && c[u].score >= thr);
+                    while (mask) {
+                        const int src = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        score_chunk(__shfl_sync(0xffffffffu, c[u].idx, src));
+                    }
                 }
             }
         }
