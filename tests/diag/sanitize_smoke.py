@@ -3,13 +3,13 @@
 latent path, dequant from the packed stream, usage histogram, KL penalty), meant to be run under
 compute-sanitizer:
 
-    compute-sanitizer --tool memcheck  python scripts/sanitize_smoke.py
-    compute-sanitizer --tool racecheck python scripts/sanitize_smoke.py
-    compute-sanitizer --tool synccheck python scripts/sanitize_smoke.py
+    compute-sanitizer --tool memcheck  python tests/diag/sanitize_smoke.py
+    compute-sanitizer --tool racecheck python tests/diag/sanitize_smoke.py
+    compute-sanitizer --tool synccheck python tests/diag/sanitize_smoke.py
 
 Round 1 on B200: 0 errors / 0 hazards with all three tools; indices equal to the oracle's."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "vq-vae-from-gaussian-vae_b200")); sys.path.insert(0, ROOT)
 import numpy as np, torch, gq_b200, oracle
 from gq_b200_host import host_codebook

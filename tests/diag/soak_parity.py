@@ -3,17 +3,17 @@
 groups and latent distributions of SURVEY 8(d) and both search modes.  The north-star bar is a near-tie
 mismatch rate < 1e-6 and zero mismatches on non-ties; this run checks ~1.5 M rows.  Prints one JSON object.
 
-    python scripts/soak_parity.py [rows_per_case]
+    python tests/diag/soak_parity.py [rows_per_case]
 """
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "vq-vae-from-gaussian-vae_b200"))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "scripts"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "diag"))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import gq_b200  # noqa: E402

@@ -4,13 +4,13 @@
 algorithmic TFLOP/s (4 g M N flop) and the fraction of the measured tensor peak, with a
 bit-exact spot check of 512 rows per point against the CPU oracle.  Prints one JSON object.
 
-    python scripts/sweep.py [--quick]
+    python tests/diag/sweep.py [--quick]
 """
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "vq-vae-from-gaussian-vae_b200"))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402

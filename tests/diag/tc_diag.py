@@ -13,7 +13,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "vq-vae-from-gaussian-vae_b200"))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")

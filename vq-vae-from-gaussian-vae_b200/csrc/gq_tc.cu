@@ -259,7 +259,7 @@ __device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G
         // plain image: fp16 rounding of both operands dominates.  Split image (g <= 4): what is left is
         // the rounding of the two lo parts (2^-22 each), the dropped lo*lo product (2^-22) and the tensor
         // core's fp32 accumulation of up to 32 products, bounded by 2^-18 P (32 truncating adds of 2^-23
-        // relative each; measured worst case on B200 is 25x below the resulting window: scripts/tc_diag.py
+        // relative each; measured worst case on B200 is 25x below the resulting window: tests/diag/tc_diag.py
         // dump_g4 reports max |error| / (W/2) = 0.02 with the 2^-17 variant of this bound).
         const float e_round = SPLIT ? 1.01f * (ldexpf(P, -18) + ldexpf(P, -20)) : 1.01f * ldexpf(P, -10);
         const float e_floor = ldexpf(sumB / scale + sumA, SPLIT ? -24 : -25);   // fp16 subnormal floors (hi and lo parts)
