@@ -86,6 +86,10 @@ int gq_codebook_create(const float *codebook, const float *nlp, int64_t N, int g
                        gq_stream_t stream, gq_codebook_t **out);
 void gq_codebook_destroy(gq_codebook_t *cb);
 int gq_codebook_set_mode(gq_codebook_t *cb, int mode);
+/* hist: device uint64[N] (caller-owned, zeroed by the caller) or NULL.  While set, every gq_quantize_latent
+ * on this codebook also accumulates the indices it emits into hist, fused into its last pass -- the
+ * reference's `all_hist += torch.histogram(indices, ...)` (eval.py:127,152-154) without another launch. */
+int gq_codebook_set_usage_histogram(gq_codebook_t *cb, uint64_t *hist);
 int64_t gq_codebook_size(const gq_codebook_t *cb);
 int gq_codebook_group(const gq_codebook_t *cb);
 const float *gq_codebook_data(const gq_codebook_t *cb); /* device fp32 [N,g] */

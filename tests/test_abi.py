@@ -141,3 +141,6 @@ def test_index_stream_entry_points_validate_without_gpu(lib):
     m = lib.gq_codebook_set_mode
     m.restype, m.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]
     assert m(None, 0) == -1 and b"handle is null" in lib.gq_last_error()
+    u2 = lib.gq_codebook_set_usage_histogram
+    u2.restype, u2.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]
+    assert u2(None, None) == -1 and b"handle is null" in lib.gq_last_error()

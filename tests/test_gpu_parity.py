@@ -613,6 +613,28 @@ def test_dequant_reads_packed_stream(gq, fmt, g, N):
             gq.dequant(h, idx.int(), layout)       # wrong width for this codebook
 
 
+@pytest.mark.parametrize("fmt,g", [("bchw", 16), ("blc", 16), ("bchw", 4), ("blc", 8)])
+def test_fused_usage_histogram(gq, fmt, g):
+    """track_usage(): the histogram accumulated inside the quantizer equals the histogram of the indices
+    it returned (eval.py:152-154), over several batches and for every output layout / group."""
+    N = 4096
+    reg = gq.GaussianQuantRegularizer(format=fmt, n_samples=N, group=g, backend="cuda").cuda().eval()
+    hist = reg.track_usage(True)
+    want = np.zeros(N, dtype=np.int64)
+    gen = torch.Generator().manual_seed(g)
+    for batch in range(3):
+        z = (torch.randn(2, 32, 8, 8, generator=gen) if fmt == "bchw" else torch.randn(2, 64, 32, generator=gen)) * 0.6
+        _, info = reg(z.cuda())
+        want = oracle.index_histogram(info["indices"].cpu().numpy(), N, want)
+    assert np.array_equal(hist.cpu().numpy(), want) and int(hist.sum()) == 3 * 2 * 64 * (16 // g)
+    usage, ent = reg.codebook_usage(hist)
+    o_usage, o_ent = oracle.usage_entropy(want)
+    assert float(usage) == pytest.approx(o_usage, rel=1e-6) and float(ent) == pytest.approx(o_ent, rel=1e-5)
+    reg.track_usage(False)
+    reg(z.cuda())
+    assert int(hist.sum()) == int(want.sum())          # switched off: the old tensor is no longer touched
+
+
 def test_module_index_stream_helpers(gq):
     reg = gq.GaussianQuantRegularizer(format="bchw", n_samples=4096, group=16, backend="cuda").cuda().eval()
     z = torch.randn(2, 32, 8, 8, device="cuda") * 0.5

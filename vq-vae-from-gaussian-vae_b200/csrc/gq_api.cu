@@ -115,6 +115,7 @@ int gq_codebook_create(const float *codebook, const float *nlp, int64_t N, int g
     int64_t off_bimg = align_up(off_nlpb + N * g * 4, 256);
     cb->kpad_robust = gq_has_robust_image(g) ? gq_image_kpad(g, true) : 0;
     cb->mode = GQ_MODE_AUTO;
+    cb->usage_hist = nullptr;
     int64_t off_bimg2 = align_up(off_bimg + cb->n_pad * cb->kpad * 2, 256);
     int64_t off_meta = align_up(off_bimg2 + cb->n_pad * cb->kpad_robust * 2, 256);
     int64_t off_wide = align_up(off_meta + 4 * (3 + 2 * kMaxG), 256);
@@ -158,6 +159,13 @@ void gq_codebook_destroy(gq_codebook_t *cb)
     cudaFree(cb->base);
     if (cb->fb_host) cudaFreeHost(const_cast<uint32_t *>(cb->fb_host));
     delete cb;
+}
+
+int gq_codebook_set_usage_histogram(gq_codebook_t *cb, uint64_t *hist)
+{
+    if (!cb) { set_error("gq_codebook_set_usage_histogram: codebook handle is null"); return GQ_ERR_INVALID; }
+    cb->usage_hist = reinterpret_cast<unsigned long long *>(hist);
+    return GQ_OK;
 }
 
 int gq_codebook_set_mode(gq_codebook_t *cb, int mode)

@@ -162,4 +162,5 @@ struct gq_codebook {
     uint32_t *wide_dev;       // device word: rows of the calls in flight whose PLAIN window exceeded the cap
     volatile uint32_t *fb_host;   // pinned, mapped: [0] = such rows in the last completed call, [1] = its row count
     uint32_t *fb_dev;         // device view of fb_host
+    unsigned long long *usage_hist;   // optional device uint64[N]: gq_quantize_latent accumulates its indices into it
 };

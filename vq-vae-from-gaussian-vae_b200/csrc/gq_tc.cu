@@ -1237,7 +1237,8 @@ frontend_kernel(const float *__restrict__ z, const float *__restrict__ eps, cons
 template <int G>
 __global__ void __launch_bounds__(256)
 finalize_kernel(const int64_t *__restrict__ idx_rows, const float *__restrict__ cb, int64_t *__restrict__ idx_out,
-                float *__restrict__ zhat_out, int64_t b, int64_t l, int ncb, int layout)
+                float *__restrict__ zhat_out, int64_t b, int64_t l, int ncb, int layout,
+                unsigned long long *__restrict__ usage_hist)
 {
     pdl_wait();
     const int64_t total = b * l * ncb;
@@ -1250,6 +1251,7 @@ finalize_kernel(const int64_t *__restrict__ idx_rows, const float *__restrict__ 
         const int64_t r = (bi * l + t) * ncb + j;
         const int64_t id = idx_rows[r];
         idx_out[i] = id;
+        if (usage_hist) atomicAdd(usage_hist + id, 1ull);   // codebook usage (eval.py:152-154), fused
         float v[G];
         load_row<G>(cb + id * G, v);
         if (layout == GQ_LAYOUT_BCHW) {
@@ -1332,8 +1334,10 @@ static int run_latent(const gq_codebook *cb, const float *z, const float *eps, i
     if (layout == GQ_LAYOUT_BLC && ncb == 1) {
         // rows are tokens and a row's codeword is the token's channel vector: the rescoring kernels write
         // the final tensors themselves, no permute / gather pass is needed
-        return run_tc<G, KPAD, SPLIT>(cb, lw.mu_r, lw.std_r, nullptr, M, idx_out, zhat_out, p, w, stats, g_w_max, stream,
-                                      /*do_prep=*/false);
+        rc = run_tc<G, KPAD, SPLIT>(cb, lw.mu_r, lw.std_r, nullptr, M, idx_out, zhat_out, p, w, stats, g_w_max, stream,
+                                    /*do_prep=*/false);
+        if (rc == GQ_OK && cb->usage_hist) rc = launch_index_histogram(idx_out, M, cb->N, cb->usage_hist, nullptr, stream);
+        return rc;
     }
     // (log std is not materialised: the settle / exact kernels take logf(std) with the libdevice function
     // the front-end and torch use, so the values are the same bits)
@@ -1341,7 +1345,8 @@ static int run_latent(const gq_codebook *cb, const float *z, const float *eps, i
                          /*do_prep=*/false);
     if (rc) return rc;
     int blocks = (int)imin((M + 255) / 256, (int64_t)device_sm_count() * 8);
-    launch_chained(finalize_kernel<G>, dim3(blocks), dim3(256), 0, stream, lw.idx_rows, cb->cb, idx_out, zhat_out, b, l, ncb, layout);
+    launch_chained(finalize_kernel<G>, dim3(blocks), dim3(256), 0, stream, lw.idx_rows, cb->cb, idx_out, zhat_out, b, l, ncb, layout,
+                   cb->usage_hist);
     count_launch(1);
     return check_launch("finalize_kernel");
 }

@@ -32,6 +32,7 @@ PROTOTYPES = {
                                    POINTER(c_void_p)]),
     "gq_codebook_destroy": (None, [c_void_p]),
     "gq_codebook_set_mode": (c_int, [c_void_p, c_int]),
+    "gq_codebook_set_usage_histogram": (c_int, [c_void_p, c_void_p]),
     "gq_codebook_size": (c_int64, [c_void_p]),
     "gq_codebook_group": (c_int, [c_void_p]),
     "gq_codebook_data": (c_void_p, [c_void_p]),

@@ -105,6 +105,15 @@ class Codebook:
             raise ValueError(f"mode must be one of {sorted(modes)}")
         check(_lib.lib().gq_codebook_set_mode(self.handle, modes[mode]), "gq_codebook_set_mode")
 
+    def set_usage_histogram(self, hist: Optional[torch.Tensor]) -> None:
+        """While set (int64 [N] CUDA tensor, accumulated in place; None to stop), every quantize_latent on
+        this codebook also counts the indices it emits -- eval.py's all_hist, fused into the last pass."""
+        if hist is not None:
+            if hist.dtype != torch.int64 or hist.numel() != self.N or not hist.is_contiguous() or hist.device != self.device:
+                raise RuntimeError("hist must be a contiguous int64 tensor of N bins on the codebook's device")
+        self._usage_hist = hist          # keep the tensor alive while the library holds its address
+        check(_lib.lib().gq_codebook_set_usage_histogram(self.handle, _ptr(hist)), "gq_codebook_set_usage_histogram")
+
     def workspace(self, M: int) -> torch.Tensor:
         need = int(_lib.lib().gq_quantize_workspace_bytes(self.handle, M))
         return self._grow(need)

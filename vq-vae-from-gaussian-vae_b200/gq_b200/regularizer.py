@@ -67,7 +67,21 @@ class _GQBase(nn.Module):
             self._cb = Codebook(ps, self.normal_log_prob, float(self.beta))
             self._cb_key = key
             self._cb.set_mode(getattr(self, "_search_mode", "auto"))
+            self._cb.set_usage_histogram(getattr(self, "_usage_hist", None))
         return self._cb
+
+    def track_usage(self, on: bool = True):
+        """Not in the reference module: accumulate the codebook-usage histogram of every eval forward inside
+        the quantizer itself (eval.py:127,152-154 keeps it on the host).  Returns the int64 [n_samples]
+        histogram tensor (None when switched off); `codebook_usage(hist)` turns it into (usage, entropy)."""
+        if on:
+            if getattr(self, "_usage_hist", None) is None:
+                self._usage_hist = torch.zeros(self.n_samples, dtype=torch.int64, device=self.prior_samples.device)
+        else:
+            self._usage_hist = None
+        if getattr(self, "_cb", None) is not None:
+            self._cb.set_usage_histogram(self._usage_hist)
+        return self._usage_hist
 
     def set_search_mode(self, mode: str) -> None:
         """Not in the reference module: search precision for groups 8 / 16 ("auto", "fast", "robust";
