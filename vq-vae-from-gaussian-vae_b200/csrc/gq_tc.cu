@@ -920,8 +920,8 @@ __device__ __forceinline__ RowIn fetch_row(int64_t r, int lane, const float *__r
 // 64-byte summaries of its <= 8 segments -- lane i takes 16-byte quarter i%4 of segment i/4; untouched
 // segments read as empty -- and mu/std/log std on lanes < g), issued one row ahead so that the round
 // trip overlaps the previous row's math.  The surviving chunks' codewords (lane = codeword) are the
-// second and last round.  Plans with more than 8 segments per row (tiny M, huge N) send every row to
-// settle_kernel instead.
+// second and last round.  Plans with more than 8 segments per row (small M: a unit is spread over many
+// CTAs) run rescore_many_kernel instead.
 template <int G>
 __global__ void __launch_bounds__(kRescoreWarps * 32, (G <= 16) ? 4 : 1)
 rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
@@ -945,20 +945,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
     const unsigned lt = (1u << lane) - 1u;
     uint32_t st_rows = 0, st_pre = 0, st_exact = 0, st_fb = 0, st_ovf = 0;
 
-    if (nseg > 8) {
-        // every row walks its full record lists in settle_kernel (unless a list overflowed)
-        for (int64_t r = warp_global; r < M; r += nwarps) {
-            bool lost = !(wrow[r] >= 0.f);
-            for (int sgi = lane; sgi < nseg; sgi += 32) lost |= rec_cnt[r * nseg + sgi] > (uint32_t)kCap;
-            lost = __any_sync(0xffffffffu, lost);
-            if (lane == 0) {
-                if (lost) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
-                else settle_rows[atomicAdd(settle_count, 1u)] = (uint32_t)r | 0x80000000u;
-            }
-            st_rows += 1;
-            st_fb += lost ? 1u : 0u;
-        }
-    } else {
+    {
         RowIn cur{}, nxt{};
         if (warp_global < M) cur = fetch_row<G>(warp_global, lane, wrow, margin_row, seg_hdr, mu, std, rec_cnt, nseg);
         for (int64_t r = warp_global; r < M; r += nwarps) {
@@ -1067,6 +1054,158 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
     }
 }
 
+// The same decision for plans with more than 8 segments per row (small M, e.g. one 256-px image = 1024 rows:
+// its 4 units are spread over all SMs, 76 short segments per row).  One warp per row, lane = segment: a
+// first pass reduces the running maxima (8 bytes per segment), a second pass visits only the segments
+// whose maximum lies inside the row's window (one or two) and collects their surviving chunk ids; the
+// prefilter and the hand-over to settle_kernel are those of rescore_kernel.  Before this kernel every
+// row of such a plan walked all its summaries in settle_kernel in the exact op order (23 us of a 59 us
+// single-image call).
+template <int G>
+__global__ void __launch_bounds__(kRescoreWarps * 32)
+rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
+                    const float *__restrict__ cb, const float *__restrict__ wrow, const float *__restrict__ margin_row,
+                    const SegHdr *__restrict__ seg_hdr, int64_t M, int64_t N, int nseg, float beta,
+                    int64_t *__restrict__ idx_out, float *__restrict__ zhat_out, uint32_t *__restrict__ fb_rows,
+                    uint32_t *__restrict__ fb_count, uint32_t *__restrict__ settle_rows, uint32_t *__restrict__ settle_chunks,
+                    uint32_t *__restrict__ settle_count, const uint32_t *__restrict__ rec_cnt,
+                    unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats)
+{
+    __shared__ __align__(16) float s_par[kRescoreWarps][2][G < 4 ? 4 : G];   // -mu, -1/den of the warp's row
+    __shared__ uint32_t s_chunks[kRescoreWarps][kMaxChunks];
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * kRescoreWarps + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * kRescoreWarps;
+    const float hb = 0.5f * beta;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t st_rows = 0, st_pre = 0, st_exact = 0, st_fb = 0, st_ovf = 0;
+
+    for (int64_t r = warp_global; r < M; r += nwarps) {
+        const float w = __ldg(wrow + r);
+        const float margin = __ldg(margin_row + r);
+        float pm = 0.f, ps = 1.f;
+        if (lane < G) {
+            pm = __ldg(mu + r * G + lane);
+            ps = __ldg(std + r * G + lane);
+        }
+        // pass 1: global running maximum over the segments that recorded something in THIS call
+        float gmax = -CUDART_INF_F;
+        bool overflow = false, lost = false;
+        for (int sg = lane; sg < nseg; sg += 32) {
+            const uint32_t recs = __ldg(rec_cnt + r * nseg + sg);
+            if (recs != 0u) {
+                const uint2 h = __ldg(reinterpret_cast<const uint2 *>(seg_hdr + r * nseg + sg));
+                gmax = fmaxf(gmax, __uint_as_float(h.x));
+                overflow |= h.y == kSegOverflow;
+                lost |= recs > (uint32_t)kCap;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+        overflow = __any_sync(0xffffffffu, overflow);
+        lost = __any_sync(0xffffffffu, lost);
+
+        int verdict = 0;   // 0 = decided here, 1 = settle (listed chunks / summaries), 2 = settle (full lists), 3 = exact scan
+        int best_idx = 0;
+        int nchunks = 0;
+        if (!(w >= 0.f) || !(gmax > -CUDART_INF_F)) verdict = 3;
+        else if (overflow) verdict = lost ? 3 : 2;
+        else {
+            const float thr = gmax - w;
+            // pass 2: only segments whose own maximum is inside the window can hold a surviving record
+            for (int sb = 0; sb < nseg; sb += 32) {
+                const int sg = sb + lane;
+                bool live = false;
+                uint32_t cnt = 0u;
+                if (sg < nseg && __ldg(rec_cnt + r * nseg + sg) != 0u) {
+                    const uint2 h = __ldg(reinterpret_cast<const uint2 *>(seg_hdr + r * nseg + sg));
+                    live = __uint_as_float(h.x) >= thr;
+                    cnt = h.y;   // <= kSurv (no overflow on this path)
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, live);
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const uint32_t c_n = __shfl_sync(0xffffffffu, cnt, src);
+                    const SegHdr *h = seg_hdr + r * nseg + sb + src;
+                    Cand c{-CUDART_INF_F, 0u};
+                    if ((uint32_t)lane < c_n) c = h->surv[lane];
+                    const bool ok = (uint32_t)lane < c_n && c.score >= thr;
+                    const unsigned m2 = __ballot_sync(0xffffffffu, ok);
+                    const int pos = nchunks + __popc(m2 & lt);
+                    if (ok && pos < kMaxChunks) s_chunks[wib][pos] = c.idx;
+                    nchunks += __popc(m2);
+                }
+            }
+            if (lane < G) {
+                const float dn = __fmul_rn(2.0f, __fmul_rn(ps, ps));
+                s_par[wib][0][lane] = -pm;          // negated: see prefilter_score_smem
+                s_par[wib][1][lane] = -(1.0f / dn);
+            }
+            __syncwarp();
+            if (nchunks > kMaxChunks) verdict = lost ? 3 : 2;   // settle_kernel walks the complete record lists
+            else if (nchunks == 0) verdict = 3;
+            else {
+                float a_best = -CUDART_INF_F, a_second = -CUDART_INF_F;
+                int n_best = 0;
+                st_pre += (uint32_t)nchunks;
+                for (int c = 0; c < nchunks; ++c) {
+                    const int64_t n0 = (int64_t)s_chunks[wib][c] * kChunk + lane;
+                    if (n0 < N) {
+                        float x0[G];
+                        load_row<G>(cb + n0 * G, x0);
+                        const float a2 = prefilter_score_smem<G>(x0, &s_par[wib][0][0], &s_par[wib][1][0], hb);
+                        if (a2 > a_best) { a_second = a_best; a_best = a2; n_best = (int)n0; }
+                        else if (a2 > a_second) a_second = a2;
+                    }
+                }
+                float g2 = a_best;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) g2 = fmaxf(g2, __shfl_xor_sync(0xffffffffu, g2, off));
+                const float lim = g2 - margin;
+                const unsigned firsts = __ballot_sync(0xffffffffu, a_best >= lim);
+                const unsigned seconds = __ballot_sync(0xffffffffu, a_second >= lim);
+                if (!(g2 > -CUDART_INF_F) || !(margin >= 0.f) || firsts == 0u) verdict = 3;   // NaN / -inf rows
+                else if (__popc(firsts) == 1 && seconds == 0u) best_idx = __shfl_sync(0xffffffffu, n_best, __ffs(firsts) - 1);
+                else verdict = 1;   // several codewords within the prefilter margin: exact op order decides
+            }
+        }
+        if (verdict == 0) {
+            if (lane == 0) idx_out[r] = (int64_t)best_idx;
+            if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
+        } else if (verdict == 3) {
+            if (lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
+        } else {
+            uint32_t slot = 0;
+            if (lane == 0) {
+                slot = atomicAdd(settle_count, 1u);
+                settle_rows[slot] = (uint32_t)r | (verdict == 2 ? 0x80000000u : 0u);
+            }
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (lane < 8) {
+                const bool listed = verdict == 1 && nchunks <= 7;
+                uint32_t v = listed ? (uint32_t)nchunks : 0xffffffffu;
+                if (lane > 0) v = (listed && lane - 1 < nchunks) ? s_chunks[wib][lane - 1] : 0u;
+                settle_chunks[(int64_t)slot * 8 + lane] = v;
+            }
+        }
+        __syncwarp();   // s_chunks / s_par are rewritten for the next row
+        st_rows += 1;
+        st_exact += verdict == 1 ? 1u : 0u;
+        st_fb += verdict == 3 ? 1u : 0u;
+        st_ovf += overflow ? 1u : 0u;
+    }
+    if (stats && lane == 0) {
+        atomicAdd(&stats[0], st_rows);
+        atomicAdd(&stats[1], st_pre * 32u);
+        atomicAdd(&stats[2], st_fb);
+        atomicAdd(&stats[3], st_ovf);
+        atomicAdd(&stats[4], st_exact);
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 template <int G, int KPAD, bool SPLIT>
 static int run_tc(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
@@ -1115,9 +1254,14 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
     {
         int64_t need = (M + kRescoreWarps - 1) / kRescoreWarps;
         int blocks = (int)imin(need, (int64_t)device_sm_count() * 8);
-        launch_chained(rescore_kernel<G>, dim3(blocks), dim3(kRescoreWarps * 32), 0, stream,
-                       mu, std, lstd, cb->cb, w.wrow, w.margin, w.seg, M, cb->N, p.nseg, cb->beta, idx, zhat, w.fb_rows,
-                       w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats);
+        if (p.nseg > 8)
+            launch_chained(rescore_many_kernel<G>, dim3(blocks), dim3(kRescoreWarps * 32), 0, stream,
+                           mu, std, lstd, cb->cb, w.wrow, w.margin, w.seg, M, cb->N, p.nseg, cb->beta, idx, zhat, w.fb_rows,
+                           w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats);
+        else
+            launch_chained(rescore_kernel<G>, dim3(blocks), dim3(kRescoreWarps * 32), 0, stream,
+                           mu, std, lstd, cb->cb, w.wrow, w.margin, w.seg, M, cb->N, p.nseg, cb->beta, idx, zhat, w.fb_rows,
+                           w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats);
         rc = check_launch("rescore_kernel");
         if (rc) return rc;
         int sblocks = (int)imin((M + 3) / 4, (int64_t)device_sm_count() * 8);
