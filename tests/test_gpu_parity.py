@@ -462,6 +462,36 @@ def test_quantize_many_units_ragged_vs_oracle(gq, N, g, M):
     assert np.array_equal(zhat.cpu().numpy(), o_zhat)
 
 
+@pytest.mark.parametrize("N,g,M,dist", [(65536, 16, 1024, "trained"), (65536, 16, 1024, "stress"), (16384, 8, 700, "trained"),
+                                        (262144, 16, 300, "trained"), (65536, 4, 2048, "trained")])
+def test_quantize_many_segment_plans(gq, N, g, M, dist):
+    """Small M: every 256-row unit is spread over many CTAs, i.e. more than 8 storage segments per row, and
+    the rescoring runs its lane-per-segment variant (rescore_many_kernel).  The codebook carries exact
+    duplicates of its first 64 codewords at its end, so rows whose best codeword is one of them are exact
+    ties that the exact-order settle kernel must resolve to the lower index (torch.argmax: first maximum).
+    Besides bit-equality with the oracle: the prefilter, not the exact-order walk, decides most rows."""
+    cb, nlp, _ = big_codebook(gq, N, g)
+    cb = cb.clone()
+    cb[-64:] = cb[:64]
+    nlp = torch.from_numpy(oracle.normal_log_prob(cb.numpy()))
+    h = gq.Codebook(cb.cuda(), nlp.cuda(), 1.0)
+    mu, std, lstd = trained_rows(M, g, seed=5 * g + M, dist=dist)
+    # aim a few rows straight at duplicated codewords
+    k = min(32, M)
+    mu[:k] = cb[:k] * (1.0 - std[:k] * std[:k])
+    stats = torch.zeros(8, dtype=torch.int32, device="cuda")
+    idx, zhat = gq.quantize_rows(h, mu.cuda(), std.cuda(), lstd.cuda(), stats=stats)
+    o_idx, o_zhat, _, o_gap = oracle.quantize(mu.numpy(), std.numpy(), lstd.numpy(), cb.numpy(), nlp.numpy())
+    got = idx.cpu().numpy()
+    bad = np.nonzero(got != o_idx)[0]
+    assert len(bad) == 0, f"{len(bad)} mismatches, rows {bad[:8]}, gaps {o_gap[bad][:8]}, stats {stats.cpu().tolist()}"
+    assert np.array_equal(zhat.cpu().numpy(), o_zhat)
+    st = stats.cpu().tolist()
+    assert st[0] == M
+    if dist == "trained" and g >= 8:
+        assert st[4] + st[2] < M // 2, f"most rows should be decided by the prefilter, stats {st}"
+
+
 @pytest.mark.parametrize("N,g,M", [(4096, 16, 3000), (65536, 16, 2048), (4096, 8, 1500)])
 def test_search_modes_agree_on_low_variance_rows(gq, N, g, M):
     """The 'stress' latents of the reference's extension test (std = |N(0,1)|, test_extension.py:18-19):
@@ -648,3 +678,35 @@ def test_module_index_stream_helpers(gq):
     usage, ent = reg.codebook_usage(hist)
     o_usage, o_ent = oracle.usage_entropy(hist.cpu().numpy())
     assert float(usage) == pytest.approx(o_usage, rel=1e-6) and float(ent) == pytest.approx(o_ent, rel=1e-5)
+
+
+def test_graphed_eval_equals_eager(gq):
+    """CUDA-graph replay of the eval branch (graphed_eval): indices / zhat equal to the eager call on fresh
+    inputs, the noise of zhat_noquant follows the default generator exactly as in eager mode and is fresh on
+    every replay; train mode refuses."""
+    reg = gq.GaussianQuantRegularizer(format="bchw", n_samples=4096, group=16, backend="cuda").cuda().eval()
+    gen = torch.Generator().manual_seed(11)
+    zs = [torch.cat([torch.randn(2, 16, 8, 8, generator=gen) * 0.8, -1.3 + 0.3 * torch.randn(2, 16, 8, 8, generator=gen)], 1).cuda()
+          for _ in range(3)]
+    run = reg.graphed_eval(zs[0])
+    for z in zs:
+        zq_e, info_e = reg(z)
+        zq_e, idx_e = zq_e.clone(), info_e["indices"].clone()
+        zq_g, info_g = run(z)
+        assert torch.equal(zq_g, zq_e) and torch.equal(info_g["indices"], idx_e)
+        assert info_g["indices"].dtype == torch.int64 and info_g["indices"].shape == (2, 1, 8, 8)
+    torch.manual_seed(5)
+    _, a = reg(zs[1])
+    nq = a["zhat_noquant"].clone()
+    torch.manual_seed(5)
+    _, b = run(zs[1])
+    assert torch.equal(nq, b["zhat_noquant"])
+    _, c = run(zs[1])
+    assert not torch.equal(nq, c["zhat_noquant"])
+    # host tensors and half precision go through the same `z.float()` as forward
+    zq_h, info_h = run(zs[2].cpu().double())
+    zq_e, info_e = reg(zs[2])
+    assert torch.equal(info_h["indices"], info_e["indices"]) and torch.equal(zq_h, zq_e)
+    reg.train()
+    with pytest.raises(RuntimeError):
+        reg.graphed_eval(zs[0])
