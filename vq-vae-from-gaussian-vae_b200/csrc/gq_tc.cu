@@ -91,7 +91,11 @@ constexpr int kThreads = (kNumEpiWarps + 4) * 32;   // epilogue warps, producer,
 constexpr int kEpiWarp0 = 0;         // epilogue warps 0..15
 constexpr int kProducerWarp = kNumEpiWarps, kIssuerWarp0 = kNumEpiWarps + 1, kAllocWarp = kNumEpiWarps + 2, kIssuerWarp1 = kNumEpiWarps + 3;
 constexpr int kCap = 32;             // chunk records per (row, segment)
-constexpr int kChunk = 32;           // columns per recorded chunk
+#ifndef GQ_CHUNK
+#define GQ_CHUNK 32
+#endif
+constexpr int kChunk = GQ_CHUNK;     // columns per recorded chunk (32 or 16); the rescoring kernels gather kChunk codewords per record
+static_assert(kChunk == 32 || kChunk == 16, "chunk width");
 constexpr int kMinStepsPerCta = 8;
 
 struct __align__(8) Cand { float score; uint32_t idx; };  // idx = chunk id (codeword / 32)
@@ -377,6 +381,11 @@ __device__ __forceinline__ float chunk_max32(const float *v)
 #ifdef GQ_EXP_NOREDUCE
     return fmaxf(v[0], v[31]);   // timing experiment only (results are wrong): how fast is the pipeline without the reduction?
 #endif
+    if constexpr (kChunk == 16) {   // 7 FMNMX3 + 1 FMNMX
+        const float c0 = max3(v[0], v[1], v[2]), c1 = max3(v[3], v[4], v[5]), c2 = max3(v[6], v[7], v[8]);
+        const float c3 = max3(v[9], v[10], v[11]), c4 = max3(v[12], v[13], v[14]);
+        return fmaxf(max3(c0, c1, c2), max3(c3, c4, v[15]));
+    }
     float a0 = max3(v[0], v[1], v[2]), a1 = max3(v[3], v[4], v[5]), a2 = max3(v[6], v[7], v[8]);
     float a3 = max3(v[9], v[10], v[11]), a4 = max3(v[12], v[13], v[14]), a5 = max3(v[15], v[16], v[17]);
     float a6 = max3(v[18], v[19], v[20]), a7 = max3(v[21], v[22], v[23]), a8 = max3(v[24], v[25], v[26]);
@@ -819,7 +828,7 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
         int best_idx = 0x7fffffff;
         auto score_chunk = [&](uint32_t chunk) {
             const int64_t n = (int64_t)chunk * kChunk + lane;
-            if (n < N) {
+            if (lane < kChunk && n < N) {
                 float x[G], nb[G];
                 load_row<G>(cb + n * G, x);
                 load_row<G>(nlpb + n * G, nb);
@@ -995,8 +1004,10 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                     float a_best = -CUDART_INF_F, a_second = -CUDART_INF_F;
                     int n_best = 0;
                     st_pre += (uint32_t)nchunks;
-                    for (int c = 0; c < nchunks; ++c) {
-                        const int64_t n0 = (int64_t)s_chunks[wib][c] * kChunk + lane;
+                    constexpr int kPer = 32 / kChunk;   // chunks per warp pass (lane = codeword)
+                    for (int c = 0; c < nchunks; c += kPer) {
+                        const int ci = c + lane / kChunk;
+                        const int64_t n0 = ci < nchunks ? (int64_t)s_chunks[wib][ci] * kChunk + lane % kChunk : N;
                         if (n0 < N) {
                             float x0[G];
                             load_row<G>(cb + n0 * G, x0);
@@ -1047,7 +1058,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
     }
     if (stats && lane == 0) {
         atomicAdd(&stats[0], st_rows);
-        atomicAdd(&stats[1], st_pre * 32u);
+        atomicAdd(&stats[1], st_pre * (uint32_t)kChunk);
         atomicAdd(&stats[2], st_fb);
         atomicAdd(&stats[3], st_ovf);
         atomicAdd(&stats[4], st_exact);
@@ -1151,8 +1162,10 @@ rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std,
                 float a_best = -CUDART_INF_F, a_second = -CUDART_INF_F;
                 int n_best = 0;
                 st_pre += (uint32_t)nchunks;
-                for (int c = 0; c < nchunks; ++c) {
-                    const int64_t n0 = (int64_t)s_chunks[wib][c] * kChunk + lane;
+                constexpr int kPer = 32 / kChunk;   // chunks per warp pass (lane = codeword)
+                for (int c = 0; c < nchunks; c += kPer) {
+                    const int ci = c + lane / kChunk;
+                    const int64_t n0 = ci < nchunks ? (int64_t)s_chunks[wib][ci] * kChunk + lane % kChunk : N;
                     if (n0 < N) {
                         float x0[G];
                         load_row<G>(cb + n0 * G, x0);
@@ -1199,7 +1212,7 @@ rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std,
     }
     if (stats && lane == 0) {
         atomicAdd(&stats[0], st_rows);
-        atomicAdd(&stats[1], st_pre * 32u);
+        atomicAdd(&stats[1], st_pre * (uint32_t)kChunk);
         atomicAdd(&stats[2], st_fb);
         atomicAdd(&stats[3], st_ovf);
         atomicAdd(&stats[4], st_exact);
