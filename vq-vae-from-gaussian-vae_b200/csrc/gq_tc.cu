@@ -932,7 +932,10 @@ __device__ __forceinline__ RowIn fetch_row(int64_t r, int lane, const float *__r
 // second and last round.  Plans with more than 8 segments per row (small M: a unit is spread over many
 // CTAs) run rescore_many_kernel instead.
 template <int G>
-__global__ void __launch_bounds__(kRescoreWarps * 32, (G <= 16) ? 4 : 1)
+#ifndef GQ_RESCORE_BLOCKS
+#define GQ_RESCORE_BLOCKS 4   // resident 256-thread blocks per SM the register budget is sized for (64 registers); 5 and 6 measured
+#endif
+__global__ void __launch_bounds__(kRescoreWarps * 32, (G <= 16) ? GQ_RESCORE_BLOCKS : 1)
 rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
                const float *__restrict__ cb, const float *__restrict__ wrow, const float *__restrict__ margin_row,
                const SegHdr *__restrict__ seg_hdr, int64_t M, int64_t N, int nseg, float beta,
