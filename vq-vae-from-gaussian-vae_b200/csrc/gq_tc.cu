@@ -1104,16 +1104,46 @@ rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std,
             pm = __ldg(mu + r * G + lane);
             ps = __ldg(std + r * G + lane);
         }
-        // pass 1: global running maximum over the segments that recorded something in THIS call
+        // pass 1: global running maximum over the segments that recorded something in THIS call.  Up to 128
+        // segments (every plan at N <= 65536) stay in registers, four per lane, with the counter and the summary
+        // head of all four loaded together (eight independent loads instead of a counter -> summary chain per trip).
+        constexpr int kSlots = 4;
+        const bool in_regs = nseg <= 32 * kSlots;
+        float rm[kSlots];
+        uint32_t cn[kSlots];
         float gmax = -CUDART_INF_F;
         bool overflow = false, lost = false;
-        for (int sg = lane; sg < nseg; sg += 32) {
-            const uint32_t recs = __ldg(rec_cnt + r * nseg + sg);
-            if (recs != 0u) {
-                const uint2 h = __ldg(reinterpret_cast<const uint2 *>(seg_hdr + r * nseg + sg));
-                gmax = fmaxf(gmax, __uint_as_float(h.x));
-                overflow |= h.y == kSegOverflow;
-                lost |= recs > (uint32_t)kCap;
+        if (in_regs) {
+            uint32_t rc[kSlots];
+            uint2 hh[kSlots];
+#pragma unroll
+            for (int u = 0; u < kSlots; ++u) {
+                const int sg = lane + 32 * u;
+                rc[u] = 0u;
+                hh[u] = make_uint2(0xff800000u, 0u);
+                if (sg < nseg) {
+                    rc[u] = __ldg(rec_cnt + r * nseg + sg);
+                    hh[u] = __ldg(reinterpret_cast<const uint2 *>(seg_hdr + r * nseg + sg));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kSlots; ++u) {
+                const bool rec = rc[u] != 0u;
+                rm[u] = rec ? __uint_as_float(hh[u].x) : -CUDART_INF_F;
+                cn[u] = rec ? hh[u].y : 0u;
+                gmax = fmaxf(gmax, rm[u]);
+                overflow |= rec && hh[u].y == kSegOverflow;
+                lost |= rc[u] > (uint32_t)kCap;
+            }
+        } else {
+            for (int sg = lane; sg < nseg; sg += 32) {
+                const uint32_t recs = __ldg(rec_cnt + r * nseg + sg);
+                if (recs != 0u) {
+                    const uint2 h = __ldg(reinterpret_cast<const uint2 *>(seg_hdr + r * nseg + sg));
+                    gmax = fmaxf(gmax, __uint_as_float(h.x));
+                    overflow |= h.y == kSegOverflow;
+                    lost |= recs > (uint32_t)kCap;
+                }
             }
         }
 #pragma unroll
@@ -1129,20 +1159,12 @@ rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std,
         else {
             const float thr = gmax - w;
             // pass 2: only segments whose own maximum is inside the window can hold a surviving record
-            for (int sb = 0; sb < nseg; sb += 32) {
-                const int sg = sb + lane;
-                bool live = false;
-                uint32_t cnt = 0u;
-                if (sg < nseg && __ldg(rec_cnt + r * nseg + sg) != 0u) {
-                    const uint2 h = __ldg(reinterpret_cast<const uint2 *>(seg_hdr + r * nseg + sg));
-                    live = __uint_as_float(h.x) >= thr;
-                    cnt = h.y;   // <= kSurv (no overflow on this path)
-                }
+            auto visit = [&](int sb, bool live, uint32_t cnt) {
                 unsigned mask = __ballot_sync(0xffffffffu, live);
                 while (mask) {
                     const int src = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const uint32_t c_n = __shfl_sync(0xffffffffu, cnt, src);
+                    const uint32_t c_n = __shfl_sync(0xffffffffu, cnt, src);   // <= kSurv (no overflow on this path)
                     const SegHdr *h = seg_hdr + r * nseg + sb + src;
                     Cand c{-CUDART_INF_F, 0u};
                     if ((uint32_t)lane < c_n) c = h->surv[lane];
@@ -1151,6 +1173,23 @@ rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std,
                     const int pos = nchunks + __popc(m2 & lt);
                     if (ok && pos < kMaxChunks) s_chunks[wib][pos] = c.idx;
                     nchunks += __popc(m2);
+                }
+            };
+            if (in_regs) {
+#pragma unroll
+                for (int u = 0; u < kSlots; ++u)
+                    if (32 * u < nseg) visit(32 * u, rm[u] >= thr, cn[u]);
+            } else {
+                for (int sb = 0; sb < nseg; sb += 32) {
+                    const int sg = sb + lane;
+                    bool live = false;
+                    uint32_t cnt = 0u;
+                    if (sg < nseg && __ldg(rec_cnt + r * nseg + sg) != 0u) {
+                        const uint2 h = __ldg(reinterpret_cast<const uint2 *>(seg_hdr + r * nseg + sg));
+                        live = __uint_as_float(h.x) >= thr;
+                        cnt = h.y;
+                    }
+                    visit(sb, live, cnt);
                 }
             }
             if (lane < G) {
