@@ -47,6 +47,10 @@ def test_no_cpu_path():
         reg.dequant(torch.zeros(1, 4, 1, dtype=torch.int64))
     with pytest.raises(NotImplementedError):
         gq_b200.quantize_rows(None, torch.zeros(2, 16), torch.ones(2, 16))
+    with pytest.raises(NotImplementedError):
+        reg.eval().graphed_eval(z)                 # the graph replay has no CPU path either
+    with pytest.raises(RuntimeError):
+        reg.train().graphed_eval(z)                # and captures the eval branch only
 
 
 @pytest.mark.parametrize("name", TRAIN_CASES)
