@@ -107,6 +107,24 @@ __device__ __forceinline__ void load_row(const float *__restrict__ p, float (&v)
 // a call switches to it when the previous calls on the codebook saw many such rows (gq_codebook_set_mode).
 __host__ __device__ constexpr bool gq_split_image(int g) { return g <= 4; }                     // always split
 __host__ __device__ constexpr bool gq_has_robust_image(int g) { return g == 8 || g == 16; }    // optional split
+// fp16 accumulators ("ACC16"): the plain fp16 image of groups 8 and 16 is contracted into fp16 TMEM
+// accumulators, read back packed (two scores per register) and max-reduced with packed 3-input fp16
+// maxima -- half the ALU work, registers and tensor-memory read time of the fp32 epilogue, which is what
+// bounded the search kernel.  The accumulator rounding (one RN per tcgen05.mma, measured) is covered by a
+// term of the per-row window that is relative to the running maximum (kWinRel16, prep_row in gq_tc.cu).
+// The codebook image of such a group stores its rows permuted inside every 64-codeword half tile so that
+// the two halves of a packed register belong to two different 32-codeword chunks (gq_acc16_image_row).
+// Split-precision images need the fp32 accumulator and keep it.  -DGQ_ACC16=0 restores the fp32 epilogue.
+#ifndef GQ_ACC16
+#define GQ_ACC16 1
+#endif
+__host__ __device__ constexpr bool gq_acc16(int g, bool split) { return GQ_ACC16 != 0 && !split && (g == 8 || g == 16); }
+// image row (position in the MMA N dimension) of codeword n: half tile h = (n % 128) / 64, chunk parity
+// p = (n % 64) / 32, lane i = n % 32  ->  column 64 h + 2 i + p, i.e. packed register i = (chunk 2h, chunk 2h+1)
+__host__ __device__ constexpr int64_t gq_acc16_image_row(int64_t n)
+{
+    return (n & ~(int64_t)63) + 2 * (n & 31) + ((n >> 5) & 1);
+}
 __host__ __device__ constexpr int gq_image_k(int g, bool split) { return split ? 6 * g : 2 * g; }
 __host__ __device__ constexpr int gq_image_kpad(int g, bool split) { return (gq_image_k(g, split) + 15) / 16 * 16; }
 __host__ __device__ constexpr int gq_image_kpad(int g) { return gq_image_kpad(g, gq_split_image(g)); }

@@ -378,12 +378,14 @@ int launch_exact_sliced(const gq_codebook *cb, const float *mu, const float *std
 __global__ void codebook_prep_kernel(const float *__restrict__ cb, const float *__restrict__ nlp_in,
                                      float *__restrict__ nlpb, __half *__restrict__ bimg,
                                      float *__restrict__ meta, int64_t N, int64_t n_pad, int g, int kpad,
-                                     float beta, int split_image, int primary)
+                                     float beta, int split_image, int primary, int permute)
 {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n_pad) return;
     const int kch = kpad / 8;
-    char *rowbase = reinterpret_cast<char *>(bimg) + (n / 8) * (int64_t)kch * 128 + (n % 8) * 16;
+    // fp16-accumulator images keep codeword n at image row gq_acc16_image_row(n) (gq_common.cuh)
+    const int64_t ir = permute ? gq_acc16_image_row(n) : n;
+    char *rowbase = reinterpret_cast<char *>(bimg) + (ir / 8) * (int64_t)kch * 128 + (ir % 8) * 16;
     float nrm2 = 0.f;
     const bool split = split_image != 0;
     for (int k = 0; k < kpad; ++k) {
@@ -436,12 +438,13 @@ int launch_codebook_prep(gq_codebook *cb, const float *nlp_in, cudaStream_t stre
     int64_t blocks = (cb->n_pad + 255) / 256;
     codebook_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(cb->cb, nlp_in, cb->nlpb, cb->bimg, cb->meta,
                                                                cb->N, cb->n_pad, cb->g, cb->kpad, cb->beta,
-                                                               gq_split_image(cb->g) ? 1 : 0, 1);
+                                                               gq_split_image(cb->g) ? 1 : 0, 1,
+                                                               gq_acc16(cb->g, gq_split_image(cb->g)) ? 1 : 0);
     codebook_meta_finish_kernel<<<1, 1, 0, stream>>>(cb->meta, cb->g);
     count_launch(2);
     if (cb->kpad_robust) {   // second, split-precision image for the robust mode (nlpb / meta already written)
         codebook_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(cb->cb, nlp_in, cb->nlpb, cb->bimg_robust, cb->meta,
-                                                                   cb->N, cb->n_pad, cb->g, cb->kpad_robust, cb->beta, 1, 0);
+                                                                   cb->N, cb->n_pad, cb->g, cb->kpad_robust, cb->beta, 1, 0, 0);
         count_launch(1);
     }
     return check_launch("codebook_prep_kernel");

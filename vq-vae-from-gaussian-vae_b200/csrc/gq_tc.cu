@@ -100,6 +100,16 @@ constexpr int kMinStepsPerCta = 8;
 
 struct __align__(8) Cand { float score; uint32_t idx; };  // idx = chunk id (codeword / 32)
 
+// fp16 accumulators add an error that is relative to the score itself: the second rounding is
+// <= 2^-11 |G~|, the first <= 2^-11 |p1| with |p1| <= min(|G~| + s U2, s amax X2) (prep_row).  With
+// d = 2^-11 (1 + 2^-9) the distance D = R - G~[n*] between a running maximum R and the reference argmax
+// satisfies D <= 2 s E0 + d (2|R| + s B1) + d (2|G~[n*]| + s B1) and |G~[n*]| <= |R| + D, hence
+// D <= w0 + kWinRel16 |R| with w0 = (2 s E0 + 2 d s B1) / (1 - 2d) (stored per row) and
+// kWinRel16 = 4 d / (1 - 2d) < 2^-9 * 1.01.  fp32 accumulators: 0.
+constexpr float kWinRel16 = 1.01f / 512.0f;
+// candidate threshold below a (running or final) maximum: everything the reference argmax can hide behind
+__device__ __forceinline__ float win_thr(float rmax, float w, float rel) { return rmax - fmaf(rel, fabsf(rmax), w); }
+
 // Per (row, segment) summary written by the epilogue thread when its piece ends: the segment's running
 // maximum and its records already filtered against that maximum (score >= runmax - w), so that the
 // rescoring kernel fetches everything it needs about a segment with one 64-byte read.
@@ -253,12 +263,23 @@ __device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G
     if (!(maxA > 0.f) || !isfinite(maxA) || !isfinite(R) || !isfinite(bnorm2)) bad = true;
     float scale = 1.f, w_scaled = -1.f, margin = 0.f;
     bool wide = false;
+    constexpr bool ACC16 = gq_acc16(G, SPLIT);
     if (!bad) {
         int ex;
         frexpf(maxA, &ex);               // maxA = f * 2^ex, f in [0.5, 1)
         scale = ldexpf(1.0f, 8 - ex);    // max |A| * scale in [128, 256)
-        const float p_norm = amax * meta[0] + sqrtf(bnorm2) * 1.000001f * meta[1];
+        const float u2 = sqrtf(bnorm2) * 1.000001f * meta[1];    // >= |sum_k b_k x_k|
+        const float p_norm = amax * meta[0] + u2;
         const float P = fminf(p_naive, p_norm);
+        if constexpr (ACC16) {
+            // fp16 accumulators: every value the tensor core writes to TMEM (the x^2 partial sum and the score)
+            // is bounded by s P (1 + 2^-10) -- keep that below 2^15 so nothing overflows fp16; the operands
+            // themselves stay below 2^15 as well
+            int exp_p;
+            frexpf(P * 1.002f, &exp_p);
+            scale = ldexpf(1.0f, imin(15 - exp_p, 15 - ex));
+            if (!isfinite(P) || !(scale > 0.f) || !isfinite(scale)) bad = true;
+        }
         const float sumB = meta[2 + 2 * kMaxG];
         // plain image: fp16 rounding of both operands dominates.  Split image (g <= 4): what is left is
         // the rounding of the two lo parts (2^-22 each), the dropped lo*lo product (2^-22) and the tensor
@@ -267,7 +288,11 @@ __device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G
         // dump_g4 reports max |error| / (W/2) = 0.02 with the 2^-17 variant of this bound).
         const float e_round = SPLIT ? 1.01f * (ldexpf(P, -18) + ldexpf(P, -20)) : 1.01f * ldexpf(P, -10);
         const float e_floor = ldexpf(sumB / scale + sumA, SPLIT ? -24 : -25);   // fp16 subnormal floors (hi and lo parts)
-        const float e_tc = e_round + e_floor + ldexpf(eA, -22);
+        // fp16 accumulators: the absolute part of the accumulator-rounding bound (kWinRel16 above), B1 = a bound
+        // on the x^2 partial sum that does not involve the score: min(U2, amax X2); plus the fp16 subnormal
+        // spacing of the stored values themselves (2^-25 in scaled units, twice)
+        const float e_acc = ACC16 ? 1.004f * ldexpf(fminf(u2, amax * meta[0]), -11) + ldexpf(1.0f / scale, -24) : 0.f;
+        const float e_tc = e_round + e_floor + ldexpf(eA, -22) + e_acc;
         constexpr float kE = (G > 16) ? 2.0f : 1.0f;   // deeper fp32 summation trees for g = 32
         const float W = 2.02f * (e_tc + kE * ldexpf(R, -20));
         margin = 2.02f * kE * 4.0f * ldexpf(R, -20);
@@ -281,7 +306,8 @@ __device__ __forceinline__ void prep_row(const float (&m)[G], const float (&s)[G
         if constexpr (gq_has_robust_image(G)) {
             // GQ_MODE_AUTO feedback: rows whose PLAIN-image window exceeds the cap (they take the exact scan
             // in fast mode), counted in either mode with one atomic per warp
-            const float w_plain = 2.02f * (1.01f * ldexpf(P, -10) + ldexpf(sumB / scale + sumA, -25) + ldexpf(eA, -22) + kE * ldexpf(R, -20));
+            const float w_plain = 2.02f * (1.01f * ldexpf(P, -10) + ldexpf(sumB / scale + sumA, -25) + ldexpf(eA, -22) + kE * ldexpf(R, -20)
+                                           + (gq_acc16(G, false) ? 1.004f * ldexpf(fminf(u2, amax * meta[0]), -11) : 0.f));
             wide = !(w_plain <= w_max);
         }
     }
@@ -406,10 +432,12 @@ __device__ __forceinline__ float chunk_max32_masked(const float *v, int n)
 
 // Slow path (~10 times per row over 2048 chunks): raise the running max / threshold and record
 // (chunk max, chunk id); the rescoring kernel re-derives the candidates of the chunk.
-__device__ __forceinline__ void epi_record(float m, uint32_t chunk, float w, float &runmax, float &thr,
-                                           uint32_t &cnt, Cand *__restrict__ list)
+template <bool ACC16>
+__device__ __forceinline__ void epi_record_t(float m, uint32_t chunk, float w, float &runmax, float &thr,
+                                             uint32_t &cnt, Cand *__restrict__ list)
 {
-    if (m > runmax) { runmax = m; thr = m - w; }
+    constexpr float rel = ACC16 ? kWinRel16 : 0.f;
+    if (m > runmax) { runmax = m; thr = win_thr(m, w, rel); }
     if (cnt < (uint32_t)kCap) list[cnt] = Cand{m, chunk};
     ++cnt;
 }
@@ -443,7 +471,36 @@ __device__ unsigned int g_tc_trace[32 * kTraceN * 4];
 #define GQ_TRACE_NEXT()
 #endif
 
-template <int KPAD, bool DUMP>
+// Maximum of the 64 scores a thread holds as 32 packed fp16 pairs: low halves = chunk 2h, high halves =
+// chunk 2h+1 of the warp's half tile (gq_acc16_image_row), so the result is (chunk max, chunk max).
+// 15 VHMNMX + 1 HMNMX2.
+__device__ __forceinline__ uint32_t chunk_max_packed(const uint32_t (&v)[32])
+{
+#ifdef GQ_EXP_NOREDUCE
+    return hmax2(v[0], v[31]);   // timing experiment only (results are wrong)
+#endif
+    uint32_t a[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = hmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    a[10] = hmax2(v[30], v[31]);
+    const uint32_t b0 = hmax3(a[0], a[1], a[2]), b1 = hmax3(a[3], a[4], a[5]), b2 = hmax3(a[6], a[7], a[8]);
+    return hmax3(hmax3(b0, b1, b2), a[9], a[10]);
+}
+__device__ __forceinline__ float half_lo(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p & 0xffffu))); }
+__device__ __forceinline__ float half_hi(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p >> 16))); }
+// (thr, thr) as fp16, rounded DOWN: a packed compare against it never misses a value >= thr
+__device__ __forceinline__ uint32_t pack_thr(float thr)
+{
+    const uint32_t h = __half_as_ushort(__float2half_rd(thr));
+    return h | (h << 16);
+}
+// nonzero iff either half of m is >= the matching half of t
+__device__ __forceinline__ uint32_t hge2_any(uint32_t m, uint32_t t)
+{
+    return __hge2_mask(*reinterpret_cast<const __half2 *>(&m), *reinterpret_cast<const __half2 *>(&t));
+}
+
+template <int KPAD, bool DUMP, bool ACC16>
 __global__ void __launch_bounds__(kThreads, 1)
 quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ b_img,
                    const float *__restrict__ wrow, SegHdr *__restrict__ seg_hdr, Cand *__restrict__ cand,
@@ -468,7 +525,10 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     auto acc_empty = [&](int st) { return bar_base + 8u * (2 * kStages + 2 + kAccStages + st); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kSlotOff);
 
-    const int warp = threadIdx.x >> 5;
+    // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so that everything the
+    // service warps derive from it -- stage counters, barrier and descriptor addresses -- lives in uniform
+    // registers instead of being moved there with R2UR in front of every tcgen05 instruction)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
     const int64_t step_begin = (int64_t)cta * steps_per_cta;
@@ -531,7 +591,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         // ===== MMA issuers, one per row block.  The whole warp runs the loop (warp-uniform control flow
         // keeps the addresses on the uniform datapath), one elected lane issues to the tensor core. =====
         const int rb = (warp == kIssuerWarp1) ? 1 : 0;
-        constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockRows, kTileN);
+        constexpr uint32_t idesc = umma_idesc_f16(kBlockRows, kTileN, /*d_f32=*/!ACC16);
         constexpr uint32_t kLbo = 128;              // K-adjacent core matrices
         constexpr uint32_t kSbo = (KPAD / 8) * 128; // next 8-row group
         // descriptor words: everything but the 14-bit start address is loop invariant
@@ -623,6 +683,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 #ifdef GQ_EXP_NOREC
             thr = CUDART_INF_F;   // timing experiment only: the record path is never taken (results are wrong)
 #endif
+            [[maybe_unused]] uint32_t thr2 = pack_thr(thr);   // fp16 accumulators: (thr, thr) rounded down
             uint32_t cnt = 0;
             const uint32_t seg_index = (uint32_t)(row * nseg + sseg);   // < 2^32, checked on the host
             int t = p.t0;
@@ -637,6 +698,39 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                 mbar_probe_wait_a(fbar, par);
                 GQ_TRACE(1);
                 tc_fence_after();
+                if constexpr (ACC16) {
+                    static_assert(!ACC16 || (kHalfCols == 64 && kChunk == 32), "fp16-accumulator epilogue: 64-column half tiles, 32-codeword chunks");
+                    // 64 fp16 scores as 32 packed registers: register i = (codeword 64*half + i, codeword 64*half + 32 + i)
+                    // of this tile, i.e. (chunk 2*half, chunk 2*half + 1) -- the codebook image is stored in that order
+                    uint32_t pv[32];
+                    tmem_ld_32x64p_sync(taddr, pv);
+                    GQ_TRACE(2);
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive_a(fbar + kEmptyOff);
+                    if constexpr (DUMP) {
+                        float *drow = dump + row * ((int64_t)tiles * kTileN) + (int64_t)t * kTileN + half * kHalfCols;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { drow[i] = half_lo(pv[i]); drow[32 + i] = half_hi(pv[i]); }
+                    }
+                    if (pad) {
+                        // columns >= N hold the zero rows of the operand image: replace them with -inf
+                        const int n_in_half = (int)(N - (int64_t)t * kTileN) - half * kHalfCols;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (i >= n_in_half) pv[i] = (pv[i] & 0xffff0000u) | 0xfc00u;
+                            if (32 + i >= n_in_half) pv[i] = (pv[i] & 0x0000ffffu) | 0xfc000000u;
+                        }
+                    }
+                    mbar_probe_a(nbar, npar);
+                    const uint32_t m2 = chunk_max_packed(pv);
+                    if (hge2_any(m2, thr2)) {
+                        const float m0 = half_lo(m2), m1 = half_hi(m2);
+                        const uint32_t c0 = (uint32_t)t * (kTileN / kChunk) + (uint32_t)(half * 2);
+                        if (m0 >= thr) epi_record_t<ACC16>(m0, c0, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
+                        if (m1 >= thr) epi_record_t<ACC16>(m1, c0 + 1u, w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
+                        thr2 = pack_thr(thr);
+                    }
+                } else {
                 float v[kHalfCols];
                 tmem_ld_cols_sync(taddr, v);
                 GQ_TRACE(2);
@@ -656,7 +750,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 #pragma unroll
                     for (int c = 0; c < kHalfCols / kChunk; ++c) {
                         const float m = chunk_max32_masked(v + c * kChunk, n_in_half - c * kChunk);
-                        if (m >= thr && c * kChunk < n_in_half) epi_record(m, (uint32_t)t * (kTileN / kChunk) + (uint32_t)(half * (kHalfCols / kChunk) + c), w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
+                        if (m >= thr && c * kChunk < n_in_half) epi_record_t<ACC16>(m, (uint32_t)t * (kTileN / kChunk) + (uint32_t)(half * (kHalfCols / kChunk) + c), w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
                     }
                 } else {
                     // Probe the NEXT use's barrier half way through the reduction: the answer (a predicate
@@ -676,9 +770,10 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                     if (mm >= thr) {
 #pragma unroll
                         for (int c = 0; c < kC; ++c)
-                            if (m[c] >= thr) epi_record(m[c], (uint32_t)t * (kTileN / kChunk) + (uint32_t)(half * (kHalfCols / kChunk) + c), w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
+                            if (m[c] >= thr) epi_record_t<ACC16>(m[c], (uint32_t)t * (kTileN / kChunk) + (uint32_t)(half * (kHalfCols / kChunk) + c), w, runmax, thr, cnt, cand + (int64_t)seg_index * kCap);
                     }
                 }
+                }   // fp32 accumulators
                 ++t;
                 GQ_TRACE(3);
                 GQ_TRACE_NEXT();
@@ -718,7 +813,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                 SegHdr *hp = &seg_hdr[seg_index];
                 uint32_t ns = 0;
                 bool ovf = cnt > (uint32_t)kCap;
-                const float keep = runmax - w;
+                const float keep = win_thr(runmax, w, ACC16 ? kWinRel16 : 0.f);
                 const uint32_t nrec = cnt < (uint32_t)kCap ? cnt : (uint32_t)kCap;
                 for (uint32_t i = 0; i < nrec; ++i) {
                     const Cand c = list[i];
@@ -800,7 +895,8 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
               const SegHdr *__restrict__ seg_hdr, const Cand *__restrict__ cand, const uint32_t *__restrict__ rec_cnt,
               const uint32_t *__restrict__ rows, const uint32_t *__restrict__ row_chunks, const uint32_t *__restrict__ nrows, int64_t N, int tiles,
               int steps_per_cta, int nseg, int64_t *__restrict__ idx_out, float *__restrict__ zhat_out,
-              uint32_t *__restrict__ fb_rows, uint32_t *__restrict__ fb_count, unsigned long long *__restrict__ fb_keys)
+              uint32_t *__restrict__ fb_rows, uint32_t *__restrict__ fb_count, unsigned long long *__restrict__ fb_keys,
+              float win_rel)
 {
     const int lane = threadIdx.x & 31;
     pdl_wait();
@@ -849,7 +945,7 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
             for (int s = lane; s < npieces; s += 32) gmax = fmaxf(gmax, seg_hdr[r * nseg + s].runmax);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
-            const float thr = gmax - wrow[r];
+            const float thr = win_thr(gmax, wrow[r], win_rel);
             static_assert(kCap == 32, "one record per lane");
             // eight segments per trip, their (independent) loads issued before any is consumed: with many
             // segments per row (small M: a unit is spread over up to 148 CTAs) this walk is the whole kernel
@@ -942,7 +1038,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                int64_t *__restrict__ idx_out, float *__restrict__ zhat_out, uint32_t *__restrict__ fb_rows,
                uint32_t *__restrict__ fb_count, uint32_t *__restrict__ settle_rows, uint32_t *__restrict__ settle_chunks,
                uint32_t *__restrict__ settle_count, const uint32_t *__restrict__ rec_cnt,
-               unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats)
+               unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats, float win_rel)
 {
     __shared__ __align__(16) float s_par[kRescoreWarps][2][G < 4 ? 4 : G];   // -mu, -1/den of the warp's row
     __shared__ uint32_t s_chunks[kRescoreWarps][kMaxChunks];
@@ -979,7 +1075,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                 if (lane < nseg) lost = rec_cnt[r * nseg + lane] > (uint32_t)kCap;
                 verdict = __any_sync(0xffffffffu, lost) ? 3 : 2;
             } else {
-                const float thr = gmax - cur.w;
+                const float thr = win_thr(gmax, cur.w, win_rel);
                 // surviving chunk ids -> shared memory
                 // quarter 0 holds survivor 0 in (z,w); quarter k>0 holds survivors 2k-1 in (x,y) and 2k in (z,w)
                 const uint32_t cnt = __shfl_sync(0xffffffffu, q.y, lane & ~3);
@@ -1083,7 +1179,7 @@ rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std,
                     int64_t *__restrict__ idx_out, float *__restrict__ zhat_out, uint32_t *__restrict__ fb_rows,
                     uint32_t *__restrict__ fb_count, uint32_t *__restrict__ settle_rows, uint32_t *__restrict__ settle_chunks,
                     uint32_t *__restrict__ settle_count, const uint32_t *__restrict__ rec_cnt,
-                    unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats)
+                    unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats, float win_rel)
 {
     __shared__ __align__(16) float s_par[kRescoreWarps][2][G < 4 ? 4 : G];   // -mu, -1/den of the warp's row
     __shared__ uint32_t s_chunks[kRescoreWarps][kMaxChunks];
@@ -1157,7 +1253,7 @@ rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std,
         if (!(w >= 0.f) || !(gmax > -CUDART_INF_F)) verdict = 3;
         else if (overflow) verdict = lost ? 3 : 2;
         else {
-            const float thr = gmax - w;
+            const float thr = win_thr(gmax, w, win_rel);
             // pass 2: only segments whose own maximum is inside the window can hold a surviving record
             auto visit = [&](int sb, bool live, uint32_t cnt) {
                 unsigned mask = __ballot_sync(0xffffffffu, live);
@@ -1270,7 +1366,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
     using L = TcSmem<KPAD>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(quantize_tc_kernel<KPAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(quantize_tc_kernel<KPAD, false, gq_acc16(G, SPLIT)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              L::kBytes);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
         attr_set = true;
@@ -1296,7 +1392,9 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
         cudaEventCreate(&ev1);
         cudaEventRecord(ev0, stream);
     }
-    launch_chained(quantize_tc_kernel<KPAD, false>, dim3(p.ctas), dim3(kThreads), L::kBytes, stream,
+    constexpr bool ACC16 = gq_acc16(G, SPLIT);
+    constexpr float win_rel = ACC16 ? kWinRel16 : 0.f;
+    launch_chained(quantize_tc_kernel<KPAD, false, ACC16>, dim3(p.ctas), dim3(kThreads), L::kBytes, stream,
                    w.a_img, (SPLIT && gq_has_robust_image(G)) ? cb->bimg_robust : cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N,
                    p.tiles, p.total_steps, p.steps_per_cta, p.nseg, nullptr);
     if (g_prof) {
@@ -1312,17 +1410,17 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
         if (p.nseg > 8)
             launch_chained(rescore_many_kernel<G>, dim3(blocks), dim3(kRescoreWarps * 32), 0, stream,
                            mu, std, lstd, cb->cb, w.wrow, w.margin, w.seg, M, cb->N, p.nseg, cb->beta, idx, zhat, w.fb_rows,
-                           w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats);
+                           w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats, win_rel);
         else
             launch_chained(rescore_kernel<G>, dim3(blocks), dim3(kRescoreWarps * 32), 0, stream,
                            mu, std, lstd, cb->cb, w.wrow, w.margin, w.seg, M, cb->N, p.nseg, cb->beta, idx, zhat, w.fb_rows,
-                           w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats);
+                           w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats, win_rel);
         rc = check_launch("rescore_kernel");
         if (rc) return rc;
         int sblocks = (int)imin((M + 3) / 4, (int64_t)device_sm_count() * 8);
         launch_chained(settle_kernel<G>, dim3(sblocks), dim3(128), 0, stream, mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.seg,
                        w.cand, w.rec_cnt, w.st_rows, w.st_chunks, w.counters + 1, cb->N, p.tiles, p.steps_per_cta, p.nseg, idx, zhat,
-                       w.fb_rows, w.counters, w.fb_keys);
+                       w.fb_rows, w.counters, w.fb_keys, win_rel);
     }
     rc = check_launch("settle_kernel");
     if (rc) return rc;
@@ -1341,7 +1439,7 @@ static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std,
                        cudaStream_t stream)
 {
     using L = TcSmem<KPAD>;
-    cudaError_t e = cudaFuncSetAttribute(quantize_tc_kernel<KPAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(quantize_tc_kernel<KPAD, true, gq_acc16(G, SPLIT)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::kBytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
     rows_prep_kernel<G, KPAD, SPLIT><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
@@ -1349,7 +1447,7 @@ static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std,
         w.counters, w.counter_bytes / 4, cb->wide_dev);
     int rc = check_launch("rows_prep_kernel");
     if (rc) return rc;
-    quantize_tc_kernel<KPAD, true><<<p.ctas, kThreads, L::kBytes, stream>>>(
+    quantize_tc_kernel<KPAD, true, gq_acc16(G, SPLIT)><<<p.ctas, kThreads, L::kBytes, stream>>>(
         w.a_img, (SPLIT && gq_has_robust_image(G)) ? cb->bimg_robust : cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N, p.tiles, p.total_steps, p.steps_per_cta, p.nseg,
         dump);
     rc = check_launch("quantize_tc_kernel<dump>");
