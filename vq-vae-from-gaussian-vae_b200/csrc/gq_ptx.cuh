@@ -281,6 +281,28 @@ __device__ __forceinline__ void mbar_wait2_a(uint32_t bar0, uint32_t par0, uint3
     if (!ok1) mbar_wait_a(bar1, par1);
 }
 
+// Three try_waits in flight at once; returns the three answers as bits 0..2 (the caller blocks on the
+// ones that were not complete yet, in the order it needs them).
+__device__ __forceinline__ uint32_t mbar_try3_a(uint32_t bar0, uint32_t par0, uint32_t bar1, uint32_t par1, uint32_t bar2,
+                                               uint32_t par2)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P, Q, R;\n\t.reg .u32 a, b, c;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 Q, [%3], %4;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 R, [%5], %6;\n\t"
+        "selp.u32 a, 1, 0, P;\n\t"
+        "selp.u32 b, 2, 0, Q;\n\t"
+        "selp.u32 c, 4, 0, R;\n\t"
+        "or.b32 a, a, b;\n\t"
+        "or.b32 %0, a, c;\n\t}"
+        : "=r"(ok)
+        : "r"(bar0), "r"(par0), "r"(bar1), "r"(par1), "r"(bar2), "r"(par2)
+        : "memory");
+    return ok;
+}
+
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -365,6 +387,18 @@ __device__ __forceinline__ void tmem_ld_wait_p(uint32_t (&v)[32])
                  : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                  :
                  : "memory");
+}
+
+// The whole 128-column accumulator tile of a warp's 32 lanes as 64 packed registers (one 32x32b.x64.pack::16b
+// load, SASS LDTM.x64.PACK16BIT) and the wait, in one asm statement.
+__device__ __forceinline__ void tmem_ld_32x128p_sync(uint32_t taddr, uint32_t (&v)[64])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr)
+        : "memory");
 }
 
 // packed fp16 pair maximum; ptxas fuses two dependent ones into the 3-input VHMNMX

@@ -77,7 +77,10 @@ using namespace gq::ptx;
 constexpr int kTileN = 128;          // codewords per B tile / MMA N
 constexpr int kBlockRows = 128;      // rows per MMA (M)
 constexpr int kUnitRows = 256;       // rows per CTA work unit (two row blocks)
-constexpr int kMaxStages = 8;        // codebook-tile ring depth (6 for the 24 KB tiles of the K = 96 image)
+#ifndef GQ_RING
+#define GQ_RING 16
+#endif
+constexpr int kMaxStages = GQ_RING;  // codebook-tile ring depth, as far as ~190 KB of shared memory go (TcSmem::kStagesL)
 constexpr int kAccStages = 4;        // TMEM accumulator stages: two private ones per row block (rb, rb + 2)
 constexpr int kTmemCols = 512;       // 4 x 128 accumulator columns (the row operands live in shared memory)
 #ifndef GQ_EPI_HALVES
@@ -85,11 +88,22 @@ constexpr int kTmemCols = 512;       // 4 x 128 accumulator columns (the row ope
 #endif
 constexpr int kHalves = GQ_EPI_HALVES;   // warps per lane quarter draining one accumulator tile (128 / kHalves columns each)
 constexpr int kNumEpiWarps = 8 * kHalves;
-constexpr int kThreads = (kNumEpiWarps + 4) * 32;   // epilogue warps, producer, 2 MMA issuers, TMEM allocator
-// Warp roles: 16 epilogue warps, then the service warps (bulk-copy producer, one MMA issuer per row
-// block, TMEM allocator).  20 warps is the most the register file holds at 96 registers per thread.
+// Warp roles: 16 epilogue warps, then the service warps: the bulk-copy producer and kIssuers MMA issuer
+// warps (the first of them also allocates tensor memory).  Four issuers = one per accumulator stage
+// (row block, A/B): an issuer's per-tile chain -- barrier probe, descriptor arithmetic, two tcgen05.mma, two
+// tcgen05.commit, loop bookkeeping, ~400 cycles of serial latency on the uniform datapath -- then has 512
+// tensor cycles to hide behind instead of 256 (scripts/tc_prof.py timeline, profiles/README.md).
+// Registers are allocated per scheduler (16 K each): 21 warps put six on one scheduler, i.e. at most 80
+// registers per thread.  The fp16-accumulator kernel needs 72 and runs four issuers; the fp32-accumulator
+// kernels (64 data registers per thread) keep two.
+#ifndef GQ_ISSUERS
+#define GQ_ISSUERS 2
+#endif
+__host__ __device__ constexpr int tc_issuers(bool acc16) { return acc16 ? GQ_ISSUERS : 2; }
+__host__ __device__ constexpr int tc_threads(bool acc16) { return (kNumEpiWarps + 1 + tc_issuers(acc16)) * 32; }
+static_assert(GQ_ISSUERS == 2 || GQ_ISSUERS == 4, "one issuer per row block, or one per accumulator stage");
 constexpr int kEpiWarp0 = 0;         // epilogue warps 0..15
-constexpr int kProducerWarp = kNumEpiWarps, kIssuerWarp0 = kNumEpiWarps + 1, kAllocWarp = kNumEpiWarps + 2, kIssuerWarp1 = kNumEpiWarps + 3;
+constexpr int kProducerWarp = kNumEpiWarps, kIssuerWarp0 = kNumEpiWarps + 1, kAllocWarp = kIssuerWarp0;
 constexpr int kCap = 32;             // chunk records per (row, segment)
 #ifndef GQ_CHUNK
 #define GQ_CHUNK 32
@@ -97,6 +111,10 @@ constexpr int kCap = 32;             // chunk records per (row, segment)
 constexpr int kChunk = GQ_CHUNK;     // columns per recorded chunk (32 or 16); the rescoring kernels gather kChunk codewords per record
 static_assert(kChunk == 32 || kChunk == 16, "chunk width");
 constexpr int kMinStepsPerCta = 8;
+#ifndef GQ_ALT_TILES
+#define GQ_ALT_TILES 1
+#endif
+constexpr bool kAltTiles = GQ_ALT_TILES != 0;   // fp16-accumulator epilogue: a warp owns one accumulator stage (0: a column half of both)
 
 struct __align__(8) Cand { float score; uint32_t idx; };  // idx = chunk id (codeword / 32)
 
@@ -371,7 +389,12 @@ rows_prep_kernel(const float *__restrict__ mu, const float *__restrict__ std, co
 template <int KPAD>
 struct TcSmem {
     static constexpr int kBTileBytes = kTileN * KPAD * 2;
-    static constexpr int kStagesL = kBTileBytes <= 16384 ? kMaxStages : 6;   // ring depth that fits 227 KB
+    // Ring depth.  The two row blocks drift apart by several tiles (each has its own accumulator handshake),
+    // and a slot is only free once BOTH have consumed it, so the prefetch distance that is left is the depth
+    // minus the drift; a bulk copy needs ~700 cycles from issue to landing (scripts/tc_prof.py).  Eight
+    // slots left the issuers waiting for tiles; sixteen cover it.  Even, so that a slot keeps its stage parity.
+    static constexpr int kFit = (190 * 1024 - 2 * (kBlockRows * KPAD * 2)) / kBTileBytes;
+    static constexpr int kStagesL = (kFit < kMaxStages ? kFit : kMaxStages) & ~1;
     static constexpr int kBOff = 0;
     // row operand of each of the two row blocks, same canonical K-major core-matrix layout as a B tile
     static constexpr int kABytes = kBlockRows * KPAD * 2;
@@ -465,16 +488,18 @@ __device__ unsigned int g_tc_trace[32 * kTraceN * 4];
 #define GQ_TRACE(slot) do { if (cta == 0 && lane == 0 && tr_it_ >= kTraceFrom && tr_it_ < kTraceFrom + kTraceN) \
         g_tc_trace[(warp * kTraceN + (tr_it_ - kTraceFrom)) * 4 + (slot)] = (unsigned int)(clock64() - tr_t0_); } while (0)
 #define GQ_TRACE_NEXT() (++tr_it_)
+#define GQ_TRACE_SET(x) (tr_it_ = (x))
 #else
 #define GQ_TRACE_DECL()
 #define GQ_TRACE(slot)
 #define GQ_TRACE_NEXT()
+#define GQ_TRACE_SET(x)
 #endif
 
 // Maximum of the 64 scores a thread holds as 32 packed fp16 pairs: low halves = chunk 2h, high halves =
 // chunk 2h+1 of the warp's half tile (gq_acc16_image_row), so the result is (chunk max, chunk max).
 // 15 VHMNMX + 1 HMNMX2.
-__device__ __forceinline__ uint32_t chunk_max_packed(const uint32_t (&v)[32])
+__device__ __forceinline__ uint32_t chunk_max_packed(const uint32_t *v)
 {
 #ifdef GQ_EXP_NOREDUCE
     return hmax2(v[0], v[31]);   // timing experiment only (results are wrong)
@@ -501,7 +526,7 @@ __device__ __forceinline__ uint32_t hge2_any(uint32_t m, uint32_t t)
 }
 
 template <int KPAD, bool DUMP, bool ACC16>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(tc_threads(ACC16), 1)
 quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ b_img,
                    const float *__restrict__ wrow, SegHdr *__restrict__ seg_hdr, Cand *__restrict__ cand,
                    uint32_t *__restrict__ rec_cnt, int64_t N, int tiles, int64_t total_steps, int steps_per_cta,
@@ -544,13 +569,14 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     if (warp == kIssuerWarp0 && lane == 0) {
         uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kBarOff);
         for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);                                  // full_b
-        for (int i = 0; i < kStages; ++i) mbar_init(&bars[kStages + i], 2);                        // empty_b: 2 issuers
+        for (int i = 0; i < kStages; ++i) mbar_init(&bars[kStages + i], 2);                        // empty_b: one arrival per row block
         for (int i = 0; i < 2; ++i) mbar_init(&bars[2 * kStages + i], 4);                          // a_full: 4 warps
         for (int i = 0; i < kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + i], 1);                           // acc_full
-        for (int i = 0; i < kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + kAccStages + i], 4 * kHalves);     // acc_empty: 8 warps
+        for (int i = 0; i < kAccStages; ++i) mbar_init(&bars[2 * kStages + 2 + kAccStages + i], (ACC16 && kAltTiles) ? 4 : 4 * kHalves);     // acc_empty: the warps draining the stage
         fence_mbar_init();
     }
     if (warp == kAllocWarp) {
+        __syncwarp();
         tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
     }
@@ -569,7 +595,9 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         uint32_t phase = 0;
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
             for (int t = p.t0; t < p.t1; ++t) {
+                GQ_TRACE(0);
                 mbar_wait_a(empty_b(stage), phase ^ 1);
+                GQ_TRACE(1);
                 if (elect_one()) {
 #ifdef GQ_EXP_HALFCOPY
                     // timing experiment only (results are wrong): every second tile is not copied at all
@@ -584,13 +612,22 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
 #endif
                 }
                 __syncwarp();
+                GQ_TRACE(2);
+                GQ_TRACE(3);
+                GQ_TRACE_NEXT();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == kIssuerWarp0 || warp == kIssuerWarp1) {
-        // ===== MMA issuers, one per row block.  The whole warp runs the loop (warp-uniform control flow
-        // keeps the addresses on the uniform datapath), one elected lane issues to the tensor core. =====
-        const int rb = (warp == kIssuerWarp1) ? 1 : 0;
+    } else if (warp >= kIssuerWarp0 && warp < kIssuerWarp0 + tc_issuers(ACC16)) {
+        // ===== MMA issuers.  Issuer iw serves row block rb = iw & 1; with four issuers it takes every second
+        // tile of that row block -- the ones that land in accumulator stage rb + 2 * (iw >> 1).  The whole warp
+        // runs the loop (warp-uniform control flow keeps the addresses on the uniform datapath), one elected
+        // lane issues to the tensor core.  Tiles are numbered by a per-CTA counter c that runs across pieces:
+        // codebook-tile ring slot c % kStages, accumulator stage parity c & 1. =====
+        const int iw = warp - kIssuerWarp0;
+        const int rb = iw & 1;
+        constexpr int kStride = tc_issuers(ACC16) / 2;       // tiles between two uses of this issuer
+        const int sub0 = kStride == 2 ? (iw >> 1) : 0;
         constexpr uint32_t idesc = umma_idesc_f16(kBlockRows, kTileN, /*d_f32=*/!ACC16);
         constexpr uint32_t kLbo = 128;              // K-adjacent core matrices
         constexpr uint32_t kSbo = (KPAD / 8) * 128; // next 8-row group
@@ -598,25 +635,29 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         constexpr uint32_t desc_hi = ((kSbo >> 4) & 0x3FFFu) | (1u << 14);           // SBO, version = 1
         const uint32_t desc_lo0 = (((smem_base + L::kBOff) >> 4) & 0x3FFFu) | (((kLbo >> 4) & 0x3FFFu) << 16);
         const uint32_t adesc_lo0 = (((smem_base + L::kAOff + rb * L::kABytes) >> 4) & 0x3FFFu) | (((kLbo >> 4) & 0x3FFFu) << 16);
+        static_assert(kStages % 2 == 0, "ring slots keep their accumulator parity");
         int64_t step = step_begin;
         Piece p;
-        int stage = 0;
-        uint32_t phase = 0;
-        int sub = 0;          // which of this row block's two accumulator stages the next use takes
-        uint32_t ep = 1;      // parity to wait for on acc_empty: passes at once on the first visit of a stage
+        uint32_t c = 0;       // tile counter of this CTA at the start of the piece
         int pi = 0;
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
             mbar_wait_a(a_full(rb), pi & 1);
             tc_fence_after();
-            for (int t = p.t0; t < p.t1; ++t) {
-                const int as = rb + 2 * sub;
+            const uint32_t c_end = c + (uint32_t)(p.t1 - p.t0);
+            uint32_t ci = kStride == 2 ? c + ((c ^ (uint32_t)sub0) & 1u) : c;   // first tile of the piece that is ours
+            for (; ci < c_end; ci += kStride) {
+                const uint32_t stage = ci % (uint32_t)kStages;
+                const uint32_t phase = (ci / (uint32_t)kStages) & 1u;
+                const uint32_t as = (uint32_t)rb + 2u * (ci & 1u);
+                const uint32_t ep = ((ci >> 1) & 1u) ^ 1u;   // u-th use of a stage (u = ci / 2) waits for its (u-1)-th drain
+                GQ_TRACE_SET(ci);
                 GQ_TRACE(0);
                 mbar_wait2_a(full_b(stage), phase, acc_empty(as), ep);
                 GQ_TRACE(1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t d = tmem_base + (uint32_t)(as * kTileN);
-                    const uint32_t desc_lo = desc_lo0 + (uint32_t)stage * (L::kBTileBytes >> 4);
+                    const uint32_t d = tmem_base + as * (uint32_t)kTileN;
+                    const uint32_t desc_lo = desc_lo0 + stage * (uint32_t)(L::kBTileBytes >> 4);
 #pragma unroll
                     for (int j = 0; j < KPAD / 16; ++j) {
                         // one K = 16 slice = two K-adjacent core matrices = 256 bytes in either operand
@@ -631,10 +672,8 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                 __syncwarp();
                 GQ_TRACE(3);
                 GQ_TRACE_NEXT();
-                sub ^= 1;
-                if (sub == 0) ep ^= 1;
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            c = c_end;
             ++pi;
         }
     } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kNumEpiWarps) {
@@ -653,6 +692,117 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
         constexpr int kHalfCols = kTileN / kHalves;
         int64_t step = step_begin;
         Piece p;
+        if constexpr (ACC16 && kAltTiles) {
+        // ---- fp16 accumulators: (row block, TILE PARITY, lane quarter).  With packed loads a whole 128-column
+        // accumulator tile is 64 registers, so a warp can own ONE accumulator stage (`half` = 0: stage A = the
+        // even tiles of the CTA's running tile count, 1: stage B) instead of a column half of both.  Its serial
+        // chain per use -- barrier, tcgen05.ld, release, two independent 32-register max trees, threshold test --
+        // then has two tile periods to hide behind, and the next barrier it needs has usually completed long
+        // before it asks (the timeline of the column-half layout showed ~290 cycles of chain per 256-cycle
+        // tile period).  Thread <-> (row, tile parity): storage segment 2 * piece + parity.
+        static_assert(kHalves == 2 && kChunk == 32, "alternate-tile epilogue");
+        constexpr uint32_t kEmptyOff2 = 8u * kAccStages;
+        const uint32_t as = (uint32_t)rb + 2u * (uint32_t)half;
+        const uint32_t fbar = acc_full(as);
+        const uint32_t obar = acc_full(rb + 2 * (half ^ 1));   // the row block's other stage
+        const uint32_t taddr = tmem_base + lane_base + as * (uint32_t)kTileN;
+        int pad_tile;
+        asm volatile("mov.b32 %0, %1;" : "=r"(pad_tile) : "r"(padded ? tiles - 1 : -1));
+        uint32_t c = 0;   // tiles this CTA has processed before the current piece
+        pdl_wait();       // the predecessor's rows / windows / segment headers are complete and visible from here on
+        while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
+            const int64_t row = (int64_t)p.unit * kUnitRows + rb * kBlockRows + q * 32 + lane;
+            const int sseg = p.seg * kHalves + half;
+            const uint32_t c_end = c + (uint32_t)(p.t1 - p.t0);
+            if (half == 0) {
+                // Row operand into shared memory.  Every MMA of the previous piece that read this row block's
+                // operand must have completed.  This warp consumed that piece's even tiles; if its last tile was
+                // an odd one, wait for that accumulator as well (a pure wait: the stage-B warps drain it).
+                if (c > 0u && ((c - 1u) & 1u)) mbar_wait_a(obar, ((c - 1u) >> 1) & 1u);
+                store_a_row_smem<KPAD>(smem_base + L::kAOff + rb * L::kABytes, q * 32 + lane, a_img + row * KPAD);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(a_full(rb));
+            }
+            const float w = wrow[row];
+            float runmax = -CUDART_INF_F;
+            float thr = (w >= 0.f) ? -CUDART_INF_F : CUDART_INF_F;
+#ifdef GQ_EXP_NOREC
+            thr = CUDART_INF_F;   // timing experiment only: the record path is never taken (results are wrong)
+#endif
+            uint32_t thr2 = pack_thr(thr);
+            uint32_t cnt = 0;
+            const uint32_t seg_index = (uint32_t)(row * nseg + sseg);   // < 2^32, checked on the host
+            Cand *list = cand + (int64_t)seg_index * kCap;
+            uint32_t ci = c + ((c ^ (uint32_t)half) & 1u);              // first tile of the piece with our parity
+            int t = p.t0 + (int)(ci - c);
+            for (; ci < c_end; ci += 2u, t += 2) {
+                const uint32_t par = (ci >> 1) & 1u;                    // this is use number ci / 2 of the stage
+                GQ_TRACE_SET(ci);
+                GQ_TRACE(0);
+                mbar_probe_wait_a(fbar, par);
+                GQ_TRACE(1);
+                tc_fence_after();
+                // register i < 32: (codeword i, codeword 32 + i) of the tile; register 32 + i: (64 + i, 96 + i)
+                uint32_t pv[64];
+                tmem_ld_32x128p_sync(taddr, pv);
+                GQ_TRACE(2);
+                tc_fence_before();
+                if (lane == 0) mbar_arrive_a(fbar + kEmptyOff2);
+                if constexpr (DUMP) {
+                    float *drow = dump + row * ((int64_t)tiles * kTileN) + (int64_t)t * kTileN;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        drow[i] = half_lo(pv[i]); drow[32 + i] = half_hi(pv[i]);
+                        drow[64 + i] = half_lo(pv[32 + i]); drow[96 + i] = half_hi(pv[32 + i]);
+                    }
+                }
+                if (t == pad_tile) {
+                    // columns >= N hold the zero rows of the operand image: replace them with -inf
+                    const int n_in = (int)(N - (int64_t)t * kTileN);
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        const int lo_cw = (i & 32) * 2 + (i & 31);
+                        if (lo_cw >= n_in) pv[i] = (pv[i] & 0xffff0000u) | 0xfc00u;
+                        if (lo_cw + 32 >= n_in) pv[i] = (pv[i] & 0x0000ffffu) | 0xfc000000u;
+                    }
+                }
+                const uint32_t ma = chunk_max_packed(pv);        // (chunk 4t, chunk 4t + 1)
+                mbar_probe_a(fbar, par ^ 1u);                    // the stage's next use: answered long before we ask again
+                const uint32_t mb = chunk_max_packed(pv + 32);   // (chunk 4t + 2, chunk 4t + 3)
+                if (hge2_any(hmax2(ma, mb), thr2)) {
+                    const float m0 = half_lo(ma), m1 = half_hi(ma), m2 = half_lo(mb), m3 = half_hi(mb);
+                    const uint32_t c0 = (uint32_t)t * (kTileN / kChunk);
+                    if (m0 >= thr) epi_record_t<ACC16>(m0, c0, w, runmax, thr, cnt, list);
+                    if (m1 >= thr) epi_record_t<ACC16>(m1, c0 + 1u, w, runmax, thr, cnt, list);
+                    if (m2 >= thr) epi_record_t<ACC16>(m2, c0 + 2u, w, runmax, thr, cnt, list);
+                    if (m3 >= thr) epi_record_t<ACC16>(m3, c0 + 3u, w, runmax, thr, cnt, list);
+                    thr2 = pack_thr(thr);
+                }
+                GQ_TRACE(3);
+            }
+            c = c_end;
+            // piece done: filter this thread's own records against its final maximum and publish the survivors
+            {
+                SegHdr *hp = &seg_hdr[seg_index];
+                uint32_t ns = 0;
+                bool ovf = cnt > (uint32_t)kCap;
+                const float keep = win_thr(runmax, w, kWinRel16);
+                const uint32_t nrec = cnt < (uint32_t)kCap ? cnt : (uint32_t)kCap;
+                for (uint32_t i = 0; i < nrec; ++i) {
+                    const Cand cd = list[i];
+                    if (cd.score >= keep) {
+                        if (ns < (uint32_t)kSurv) hp->surv[ns] = cd;
+                        else ovf = true;
+                        ++ns;
+                    }
+                }
+                hp->runmax = runmax;
+                hp->cnt = ovf ? kSegOverflow : ns;
+                rec_cnt[seg_index] = cnt;
+            }
+        }
+        } else {
         // This row block's two private stages A = rb and B = rb + 2: barrier address, TMEM address and
         // the phase parity of the next use.  acc_empty(s) sits at a constant offset from acc_full(s).
         constexpr uint32_t kEmptyOff = 8u * kAccStages;
@@ -828,6 +978,7 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
                 rec_cnt[seg_index] = cnt;
             }
         }
+        }   // column-half epilogue
     }
 
     tc_fence_before();
@@ -1394,7 +1545,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
     }
     constexpr bool ACC16 = gq_acc16(G, SPLIT);
     constexpr float win_rel = ACC16 ? kWinRel16 : 0.f;
-    launch_chained(quantize_tc_kernel<KPAD, false, ACC16>, dim3(p.ctas), dim3(kThreads), L::kBytes, stream,
+    launch_chained(quantize_tc_kernel<KPAD, false, ACC16>, dim3(p.ctas), dim3(tc_threads(ACC16)), L::kBytes, stream,
                    w.a_img, (SPLIT && gq_has_robust_image(G)) ? cb->bimg_robust : cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N,
                    p.tiles, p.total_steps, p.steps_per_cta, p.nseg, nullptr);
     if (g_prof) {
@@ -1447,7 +1598,7 @@ static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std,
         w.counters, w.counter_bytes / 4, cb->wide_dev);
     int rc = check_launch("rows_prep_kernel");
     if (rc) return rc;
-    quantize_tc_kernel<KPAD, true, gq_acc16(G, SPLIT)><<<p.ctas, kThreads, L::kBytes, stream>>>(
+    quantize_tc_kernel<KPAD, true, gq_acc16(G, SPLIT)><<<p.ctas, tc_threads(gq_acc16(G, SPLIT)), L::kBytes, stream>>>(
         w.a_img, (SPLIT && gq_has_robust_image(G)) ? cb->bimg_robust : cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N, p.tiles, p.total_steps, p.steps_per_cta, p.nseg,
         dump);
     rc = check_launch("quantize_tc_kernel<dump>");
