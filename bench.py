@@ -6,21 +6,32 @@
 
 A "step" is one eval-mode pass of the drop-in GaussianQuantRegularizer over one batch of
 synthetic latents: BASELINE.json configs[1], z[64, 32, 32, 32] (batch 64 at 256 px -> 65 536
-tokens, one group of 16 per token) against the 65 536 x 16 iid-Gaussian codebook:
-prologue (clamp/exp/log/randn, torch), fused tcgen05 search + exact re-score, dequant.
+tokens, one group of 16 per token) against the 65 536 x 16 iid-Gaussian codebook: fused front-end
+(clamp/exp/log, row operands), tcgen05 search + exact re-score, gather (dequant).
 
   value : tokens/s with the latents resident in HBM (module forward), CUDA events, max over ranks
   e2e   : the same call fed from pinned host memory, H2D of z and D2H of the indices inside
           the timed region
   roofline : the search kernel's algorithmic flops 4*g*M*N over its own CUDA-event time
-             (events recorded inside the library around that one launch), against
+             (events recorded inside the library around that one launch; max over ranks), against
              MEASURED_PEAKS.json bf16 dense
   cpu_baseline : oracle/gq_oracle.c (OpenMP C port of the reference torch path) on the host
              cores, on a bounded row sample of the same workload
 
+Beside the headline the same JSON line carries (all measured in this run):
+  per_rank       : step / kernel / e2e time and SM clock of every rank (N > 1)
+  exchange       : (N > 1) the two NCCL exchanges north_star names, inside a timed loop: all-gather of the
+                   step's indices (int64 and the packed uint16 stream) and the one-collective KL-stat fold
+  scaling_strong : a FIXED global problem (1 048 576 rows) split evenly over the N ranks
+  sustained      : (N = 1) the step looped for >= 3 s, against the sustained tensor peak
+  configs        : (N = 1) BASELINE.json configs[2..4] + the reference's own extension-test shape: g = 4
+                   sub-codebooks, the train-step KL kernels (GB/s of algorithmic bytes) with a CPU train-branch
+                   baseline, dequant, stress latents, and a condensed (N, M) sweep
+
 Multi-GPU (torchrun, one rank per GPU): rows shard by batch, every rank quantizes its own
-64-image batch (weak scaling); the path has no exchange step (the reference runs pure replicas,
-eval.py:97-107), so no collective sits in the timed region.
+64-image batch (weak scaling); the data path itself has no exchange step (the reference runs pure
+replicas, eval.py:97-107), so the headline's timed region holds no collective; `exchange` measures
+what the optional all-gather / KL fold cost on top.
 """
 import argparse
 import json
@@ -29,7 +40,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -47,14 +57,20 @@ METRIC = "gq_quantize_tokens_per_s"
 UNIT = "tokens/s"
 WORKLOAD = ("configs[1]: sd3unet_gq_0.25 regularizer pass (quantize + dequant), batch 64 @256px "
             "-> 65536 tokens x 65536x16 codebook")
+STRONG_ROWS = 1 << 20
+# SURVEY.md 8(a) A3 [probe]: the unmodified reference torch path (backend="torch", eval) in the build container
+TORCH_REFERENCE_PROBE = {"value": 140.0, "unit": UNIT, "cores": 8, "kind": "reference (stated constant)",
+                         "provenance": "SURVEY.md 8(a) A3 [probe]: unmodified pit/quantization/gaussian.py, torch 2.11 CPU, "
+                                       "8 Xeon cores of the build container, one 1024-row call (7 s); the python reference "
+                                       "cannot travel to the GPU box, so this is not re-measured here"}
 
 
-def synth_latents(batch, seed):
+def synth_latents(batch, seed, channels=CHANNELS):
     """D-trained latents of SURVEY.md 8(d): mu ~ N(0, 0.75), logvar ~ N(-1.386, 0.3^2)."""
     import torch
     gen = torch.Generator().manual_seed(seed)
-    mu = torch.randn(batch, CHANNELS, HW, HW, generator=gen) * 0.866
-    lv = -1.386 + 0.3 * torch.randn(batch, CHANNELS, HW, HW, generator=gen)
+    mu = torch.randn(batch, channels, HW, HW, generator=gen) * 0.866
+    lv = -1.386 + 0.3 * torch.randn(batch, channels, HW, HW, generator=gen)
     return torch.cat([mu, lv], 1)
 
 
@@ -92,6 +108,7 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        """Terminate the sampler (nvidia-smi block-buffers a file: its samples are complete only now) and parse them."""
         rows = []
         if self.p is None:
             return rows
@@ -100,6 +117,7 @@ class ClockSampler:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
+        self.p = None
         self.f.flush()
         self.f.seek(0)
         import datetime
@@ -113,7 +131,10 @@ class ClockSampler:
                              [nm for nm, v in zip(self.NAMES, parts[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-        os.unlink(self.f.name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
         return rows
 
     @staticmethod
@@ -130,12 +151,27 @@ class ClockSampler:
         return out
 
 
+def pin_to_gpu_numa(gpu_index):
+    """Bind this process to the CPUs next to its GPU before any pinned host buffer is allocated (first-touch
+    places the pages on that NUMA node).  At 8 ranks the 8 x 8 MB-per-step H2D streams otherwise share one
+    socket's memory controllers and inter-socket link; returns the CPU list or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"{cpus[0]}-{cpus[-1]} ({len(cpus)} cpus)" if cpus else None
+    except Exception:
+        return None
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of the reference torch path (the Python reference itself cannot
     travel to the GPU box), all host threads, a bounded row sample of the same workload per step."""
     if rank != 0:
         return
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     import oracle
     from gq_b200_host import host_codebook
@@ -164,11 +200,385 @@ def run_reference(args, rank, world):
         "config": {"workload": WORKLOAD, "n_samples": N_SAMPLES, "group": GROUP, "sample_rows": rows,
                    "note": "CPU port of the reference torch path (oracle/gq_oracle.c, OpenMP); the python reference "
                            "is absent on the GPU box"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample,
+                         "reference_torch_probe": TORCH_REFERENCE_PROBE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+class Ctx:
+    """Everything the measurement legs share."""
+
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.args, self.rank, self.world = args, rank, world
+        self.dev = torch.device("cuda", local_rank)
+        self.pk = peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def gather_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world == 1:
+            return [[float(x)] for x in t.tolist()]
+        out = self.torch.empty(self.world * len(vals), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_gather_into_tensor(out, t)
+        m = out.view(self.world, len(vals)).t().tolist()
+        return [[float(x) for x in row] for row in m]
+
+    def time_loop(self, fn, iters, warm=3, bracket=True):
+        """ms per call of fn(k): `warm` untimed calls, then `iters` timed by ONE CUDA event pair on the current
+        stream, barrier + synchronize on both sides when `bracket`."""
+        torch = self.torch
+        for k in range(warm):
+            fn(k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if bracket:
+            self.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for k in range(iters):
+            fn(k)
+        e1.record()
+        torch.cuda.synchronize()
+        if bracket:
+            self.barrier()
+        return e0.elapsed_time(e1) / iters
+
+    def graph_ms(self, fn, inner=20, reps=5):
+        """GPU time per call of fn(k) with the host taken out: `inner` calls are captured ONCE in a CUDA graph
+        (allocations land in the graph's private pool) and the replay is timed with CUDA events.  For kernels of
+        a few microseconds, whose eager launch path (python + torch allocator + ctypes) is several times longer."""
+        torch = self.torch
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for k in range(3):
+                fn(k)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for k in range(inner):
+                fn(k)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (reps * inner)
+
+    def kernel_ms(self, fn, iters=6):
+        """Search-kernel time of fn(): CUDA events inside the library around that one launch, every launch."""
+        import ctypes
+        from gq_b200 import _lib
+        L = _lib.lib()
+        self.sync()
+        L.gq_profile_enable(1)
+        for k in range(iters):
+            fn(k)
+        self.sync()
+        L.gq_profile_enable(0)
+        tot, cnt = ctypes.c_double(0.0), ctypes.c_int(0)
+        L.gq_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
+        return tot.value / max(cnt.value, 1), cnt.value
+
+
+def pool_for(ctx, make, nbytes, min_bytes=160e6):
+    """Input pool larger than the 126 MB L2, rotated so that no step finds its latents cached."""
+    n = max(2, int(min_bytes // nbytes) + 1)
+    return [make(i).to(ctx.dev) for i in range(n)]
+
+
+def leg_exchange(ctx, reg, pool):
+    """N > 1: the exchanges north_star names, each inside its own timed loop (max over ranks)."""
+    import gq_b200
+    from gq_b200 import distributed as gd
+    from gq_b200.ops import GQ_LAYOUT_BCHW
+    torch, world, B = ctx.torch, ctx.world, pool[0].shape[0]
+    M = B * HW * HW
+    steps = max(10, min(ctx.args.steps, 100))
+    res = {}
+
+    def q_gather(k):
+        _, info = reg(pool[k % len(pool)])
+        return gd.all_gather_indices(info["indices"], B * world)
+
+    def q_gather_packed(k):
+        _, info = reg(pool[k % len(pool)])
+        return gd.all_gather_indices(reg.pack_indices(info["indices"]), B * world)
+
+    # correctness of what is being timed: every rank finds its own shard in the gathered tensor
+    _, info = reg(pool[0])
+    full = gd.all_gather_indices(info["indices"], B * world)
+    fullp = gd.all_gather_indices(reg.pack_indices(info["indices"]), B * world)
+    lo = ctx.rank * B
+    ok = bool(torch.equal(full[lo:lo + B], info["indices"])) and bool(torch.equal(reg.unpack_indices(fullp), full))
+    ok = bool(ctx.max_over_ranks(0.0 if ok else 1.0)[0] == 0.0)
+
+    idx = info["indices"]
+    packed = reg.pack_indices(idx)
+    for name, fn, payload in (("quantize_allgather_int64", q_gather, idx), ("quantize_allgather_packed_u16", q_gather_packed, packed)):
+        ms = ctx.max_over_ranks(ctx.time_loop(fn, steps))[0]
+        coll = ctx.max_over_ranks(ctx.time_loop(lambda k, t=payload: gd.all_gather_indices(t, B * world), steps))[0]
+        res[name] = {"value": world * M / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                     "bytes_per_rank": payload.numel() * payload.element_size(), "collective_us": coll * 1e3}
+    # train branch: KL kernel + the one-collective fold of its partial sums (gaussian.py:83-98 over the global batch)
+    z = pool[0]
+    eps = torch.randn(B, CHANNELS, HW, HW, device=ctx.dev)
+
+    def kl_fold(k):
+        _, _, st = gq_b200.kl_penalty(pool[k % len(pool)], eps, GROUP, GQ_LAYOUT_BCHW)
+        return gd.global_kl_stats(st, M, B * world, 1.0)
+
+    _, _, st = gq_b200.kl_penalty(z, eps, GROUP, GQ_LAYOUT_BCHW)
+    ms = ctx.max_over_ranks(ctx.time_loop(kl_fold, steps))[0]
+    coll = ctx.max_over_ranks(ctx.time_loop(lambda k: gd.global_kl_stats(st, M, B * world, 1.0), steps))[0]
+    res["kl_fwd_plus_stat_fold"] = {"ms_per_step": ms, "collective_us": coll * 1e3, "bytes_per_rank": 40,
+                                    "note": "one all_gather_into_tensor of 5 float64 per rank + local fold (torch ops included)"}
+    res["verified"] = ok
+    res["steps"] = steps
+    res["backend"] = "nccl"
+    return res
+
+
+def leg_strong(ctx, reg):
+    """Fixed global problem: STRONG_ROWS rows (1024 images) split evenly over the ranks."""
+    world = ctx.world
+    b_local = STRONG_ROWS // (HW * HW) // world
+    z_bytes = b_local * 2 * CHANNELS * HW * HW * 4
+    pool = pool_for(ctx, lambda i: synth_latents(b_local, 5000 + 31 * ctx.rank + i), z_bytes)
+    steps = 12
+    ms = ctx.time_loop(lambda k: reg(pool[k % len(pool)]), steps)
+    per_rank = ctx.gather_ranks(ms)[0]
+    ms_max = max(per_rank)
+    del pool
+    ctx.torch.cuda.empty_cache()
+    return {"scaling": "strong", "global_rows": STRONG_ROWS, "rows_per_gpu": b_local * HW * HW, "steps": steps,
+            "ms_per_step": ms_max, "value": STRONG_ROWS / (ms_max * 1e-3), "unit": UNIT, "ms_per_step_per_rank": per_rank,
+            "l2": f"inputs rotate over {max(2, int(160e6 // z_bytes) + 1)} buffers of {z_bytes / 1e6:.1f} MB per rank (> 126 MB L2)"}
+
+
+def leg_sustained(ctx, step, pool, flops, seconds):
+    """The headline step looped for >= `seconds` of device time; against the sustained tensor peak."""
+    import ctypes
+    from gq_b200 import _lib
+    torch = ctx.torch
+    L = _lib.lib()
+    chunk = 1000
+    L.gq_profile_enable(64)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_epoch0 = time.time()
+    t0 = time.perf_counter()
+    e0.record()
+    n = 0
+    while True:
+        for k in range(chunk):
+            step(pool[(n + k) % len(pool)])
+        n += chunk
+        torch.cuda.current_stream().synchronize()
+        if time.perf_counter() - t0 >= seconds:
+            break
+    e1.record()
+    torch.cuda.synchronize()
+    t_epoch1 = time.time()
+    L.gq_profile_enable(0)
+    tot, cnt = ctypes.c_double(0.0), ctypes.c_int(0)
+    L.gq_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
+    ms = e0.elapsed_time(e1) / n
+    kms = tot.value / max(cnt.value, 1)
+    M = pool[0].shape[0] * HW * HW
+    ach = flops / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+    return {"seconds": e0.elapsed_time(e1) * 1e-3, "steps": n, "ms_per_step": ms, "value": M / (ms * 1e-3), "unit": UNIT,
+            "kernel_ms": kms, "kernel_launches_timed": cnt.value, "achieved_tflops": ach,
+            "frac_of_sustained_peak": ach / ctx.pk["bf16_tflops_sustained"], "frac_of_burst_peak": ach / ctx.pk["bf16_tflops"],
+            "whole_step_tflops": flops / (ms * 1e-3) / 1e12, "window": (t_epoch0, t_epoch1)}
+
+
+def leg_configs(ctx):
+    """N = 1: BASELINE.json configs[2..4] and the reference's extension-test shape, each with its own roofline."""
+    import gq_b200
+    from gq_b200.ops import GQ_LAYOUT_BCHW, GQ_LAYOUT_BLC
+    torch, dev, pk = ctx.torch, ctx.dev, ctx.pk
+    out = {}
+    SMS, GHZ = 148, 1.965e9
+
+    def quantizer_case(reg, zs, g, ncb, iters):
+        M = zs[0].shape[0] * HW * HW * ncb
+        ms = ctx.time_loop(lambda k: reg(zs[k % len(zs)]), iters, bracket=False)
+        kms, kc = ctx.kernel_ms(lambda k: reg(zs[k % len(zs)]))
+        fl = 4.0 * g * M * N_SAMPLES
+        return {"rows": M, "ms_per_step": ms, "rows_per_s": M / (ms * 1e-3), "spatial_tokens_per_s": M / ncb / (ms * 1e-3),
+                "roofline": {"bound": "tensor", "kernel_ms": kms, "kernel_launches_timed": kc, "achieved": fl / (kms * 1e-3) / 1e12 if kms else None,
+                             "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / (kms * 1e-3) / 1e12 / pk["bf16_tflops"] if kms else None,
+                             "algorithmic_flops_per_launch": fl}}
+
+    # ---- configs[2]: sd3unet_gq_1.00 (configs/sd3unet_gq_1.00.yaml:27-33): group 4, four sub-codebooks per token ----
+    try:
+        reg4 = gq_b200.GaussianQuantRegularizer(format="bchw", n_samples=N_SAMPLES, group=4, backend="cuda").to(dev).eval()
+        c2 = {"workload": "sd3unet_gq_1.00: g=4, ncb=4, 65536x4 codebook, z[b,32,32,32] bchw; split-precision image, K = 6g -> 32 "
+                          "(the tensor cost of g=16), fp32 accumulators"}
+        for b, iters in ((32, 20), (256, 6)):
+            zs = pool_for(ctx, lambda i, b=b: synth_latents(b, 300 + i), b * 32 * HW * HW * 4)
+            r = quantizer_case(reg4, zs, 4, 4, iters)
+            # what bounds it: the split image costs one 128x128x32 MMA pair per tile (128 tensor cycles / 16384 scores);
+            # the fp32 epilogue's row max needs 0.5 three-input max per score at 2.8 cycles per warp instruction
+            # per scheduler (scripts/ubench/hmax_tput.cu)
+            r["bounds_rows_per_s"] = {"tensor_pipe_k32": SMS * GHZ * 128.0 / N_SAMPLES,
+                                      "fp32_max_reduce": SMS * 4 * GHZ * (64.0 / 2.8) / N_SAMPLES}
+            r["frac_of_max_reduce_bound"] = r["rows_per_s"] / r["bounds_rows_per_s"]["fp32_max_reduce"]
+            c2[f"b{b}"] = r
+            del zs
+        del reg4
+        out["configs[2]"] = c2
+    except Exception as e:  # noqa: BLE001
+        out["configs[2]"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: bsqvit_gq_0.25 (configs/bsqvit_gq_0.25.yaml:27-33) train step at z[256,1024,32] blc ----
+    try:
+        b, l, C = 256, 1024, 16
+        gen = torch.Generator().manual_seed(7)
+        zs = [torch.cat([torch.randn(b, l, C, generator=gen) * 0.866, -1.386 + 0.3 * torch.randn(b, l, C, generator=gen)], 2).to(dev)
+              for _ in range(5)]
+        eps = [torch.randn(b, l, C, device=dev) for _ in range(5)]
+        gz = [torch.randn(b, l, C, device=dev) for _ in range(5)]
+        fwd_bytes = b * l * C * (8 + 4 + 4)
+        bwd_bytes = b * l * C * (8 + 4 + 4 + 8)     # z, eps, grad_zhat in; grad_z out (the per-group weights are 1/16 of that)
+
+        from gq_b200 import _lib
+        from gq_b200.ops import _ptr, _stream
+        Lc = _lib.lib()
+        ncb = C // GROUP
+        zh = torch.empty(b, l, C, device=dev)
+        wo = torch.empty(b * l * ncb, device=dev)
+        stt = torch.empty(8, device=dev)
+        gzo = torch.empty(b, l, 2 * C, device=dev)
+        gkl = torch.full((), 0.1, device=dev)
+        wsb = torch.empty(int(Lc.gq_kl_workspace_bytes(b, l, C)), dtype=torch.uint8, device=dev)
+
+        def kl_fwd(k):     # the C entry point on preallocated tensors: what the autograd function launches
+            _lib.check(Lc.gq_kl_fwd(_ptr(zs[k % 5]), _ptr(eps[k % 5]), _ptr(zh), _ptr(wo), _ptr(stt), b, l, C, GROUP, GQ_LAYOUT_BLC,
+                                    -30.0, 20.0, 16.0, 0.5, 1.0, 1.0, 1.0, _ptr(wsb), wsb.numel(), _stream()), "gq_kl_fwd")
+
+        def kl_bwd(k):
+            _lib.check(Lc.gq_kl_bwd(_ptr(zs[k % 5]), _ptr(eps[k % 5]), _ptr(wo), _ptr(gz[k % 5]), _ptr(gkl), _ptr(gzo), b, l, C, GROUP,
+                                    GQ_LAYOUT_BLC, -30.0, 20.0, 1.0, _stream()), "gq_kl_bwd")
+
+        ms_f = ctx.graph_ms(kl_fwd)
+        ms_b = ctx.graph_ms(kl_bwd)
+        zr = [z.clone().requires_grad_(True) for z in zs]
+        regt = gq_b200.GaussianQuantRegularizer(format="blc", n_samples=N_SAMPLES, group=GROUP, backend="cuda").to(dev)
+        regt.train()
+
+        def train_step(k):
+            z = zr[k % 5]
+            zh, info = regt(z)
+            (0.1 * info["kl_loss"] + (zh * gz[k % 5]).sum()).backward()
+            z.grad = None
+
+        ms_mod = ctx.time_loop(train_step, 20, bracket=False)
+        regt.eval()
+        with torch.no_grad():
+            qcase = quantizer_case(regt, zs, GROUP, 1, 6)
+        c3 = {"workload": "bsqvit_gq_0.25 train step: z[256,1024,32] blc, g=16 (M = 262144 groups)",
+              "kl_fwd": {"ms": ms_f, "algorithmic_bytes": fwd_bytes, "gbs": fwd_bytes / ms_f / 1e6, "frac_of_hbm_peak": fwd_bytes / ms_f / 1e6 / pk["hbm_gbs"]},
+              "kl_bwd": {"ms": ms_b, "algorithmic_bytes": bwd_bytes, "gbs": bwd_bytes / ms_b / 1e6, "frac_of_hbm_peak": bwd_bytes / ms_b / 1e6 / pk["hbm_gbs"]},
+              "kl_timing": "gq_kl_fwd / gq_kl_bwd through the C ABI on preallocated tensors, 20 calls captured in a CUDA graph and replayed (GPU time "
+                           "without the python launch path, which is longer than these kernels)",
+              "peak_hbm_gbs": pk["hbm_gbs"], "l2": "five 33.5 MB latents + noise + grads in rotation (> 126 MB L2)",
+              "module_train_step_ms": ms_mod, "module_note": "drop-in module forward (randn + KL kernel + ONE D2H for the lambda controller) + backward",
+              "quantizer_eval_same_shape": qcase}
+        try:
+            import oracle
+            oracle.set_num_threads(0)
+            zc = zs[0].cpu().numpy()
+            oracle.kl(zc[:8], GROUP, 16, 0.5, 1.0, 1.0, 1.0)
+            t0 = time.perf_counter()
+            oracle.kl(zc, GROUP, 16, 0.5, 1.0, 1.0, 1.0)
+            c3["cpu_train_branch"] = {"ms": (time.perf_counter() - t0) * 1e3, "kind": "port", "cores": oracle.num_threads(),
+                                      "sample": "the full z[256,1024,32] forward (kl2, band weights, reduction); reference torch CPU probe: 31 ms fwd / 11 ms bwd on 8 cores (SURVEY 8d)"}
+        except Exception as e:  # noqa: BLE001
+            c3["cpu_train_branch"] = {"error": repr(e)}
+        out["configs[3]"] = c3
+        del zs, eps, gz, zr, regt
+    except Exception as e:  # noqa: BLE001
+        out["configs[3]"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+
+    # ---- dequant (gaussian.py:162-178) ----
+    try:
+        reg = gq_b200.GaussianQuantRegularizer(format="bchw", n_samples=N_SAMPLES, group=GROUP, backend="cuda").to(dev).eval()
+        b = 256
+        idxs = [torch.randint(0, N_SAMPLES, (b, 1, HW, HW), device=dev) for _ in range(12)]
+        nbytes = b * HW * HW * (8 + 4 * GROUP)
+        cbk = reg._codebook()
+        ms = ctx.graph_ms(lambda k: gq_b200.dequant(cbk, idxs[k % 12], GQ_LAYOUT_BCHW))
+        pk16 = [reg.pack_indices(i) for i in idxs]
+        nb16 = b * HW * HW * (2 + 4 * GROUP)
+        ms16 = ctx.graph_ms(lambda k: gq_b200.dequant(cbk, pk16[k % 12], GQ_LAYOUT_BCHW))
+        out["dequant"] = {"workload": "indices [256,1,32,32] -> zhat [256,16,32,32] (codebook L2-resident, not counted)",
+                          "int64": {"ms": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / pk["hbm_gbs"]},
+                          "packed_u16": {"ms": ms16, "algorithmic_bytes": nb16, "gbs": nb16 / ms16 / 1e6, "frac_of_hbm_peak": nb16 / ms16 / 1e6 / pk["hbm_gbs"]},
+                          "note": "20 calls captured in a CUDA graph and replayed (GPU time without the python launch path); twelve index tensors in rotation"}
+        # ---- the reference's own extension benchmark shape (gq_cuda_extension/test/test_extension.py:10-22) ----
+        M = 262144
+        gen = torch.Generator().manual_seed(3)
+        mu = torch.randn(M, GROUP, generator=gen).to(dev)
+        std = torch.abs(torch.randn(M, GROUP, generator=gen)).clamp_min(1e-12).to(dev)
+        ms = ctx.time_loop(lambda k: gq_b200.quantize_rows(cbk, mu, std), 5, warm=4, bracket=False)
+        stats = torch.zeros(8, dtype=torch.int32, device=dev)
+        gq_b200.quantize_rows(cbk, mu, std, stats=stats)
+        st = stats.cpu().tolist()
+        out["stress_test_extension_shape"] = {
+            "workload": "test_extension.py:10-22 shape: b = 262144 rows, dim 16, 65536 codewords, mu ~ N(0,1), std = |N(0,1)|",
+            "ms": ms, "rows_per_s": M / (ms * 1e-3), "frac_of_tensor_peak_whole_call": 4.0 * GROUP * M * N_SAMPLES / (ms * 1e-3) / 1e12 / pk["bf16_tflops"],
+            "rows_to_exact_scan": st[2], "rows_settled_in_exact_order": st[4], "search_mode": "auto (settled by the warm-up calls)"}
+        # ---- configs[4]: condensed sweep, rows resident in HBM, D-trained rows ----
+        sweep = []
+        from gq_b200.regularizer import prior_samples
+        for N in (4096, 65536, 262144):
+            cbn = prior_samples(N, GROUP, 42).float().to(dev)
+            cbh = gq_b200.Codebook(cbn, None, 1.0)
+            for M in (1024, 16384, 262144, 1048576):
+                gen = torch.Generator().manual_seed(M % 1000 + N % 97)
+                mu = (torch.randn(M, GROUP, generator=gen) * 0.866).to(dev)
+                std = torch.exp(0.5 * (-1.386 + 0.3 * torch.randn(M, GROUP, generator=gen))).to(dev)
+                iters = 30 if M <= 16384 else (8 if M <= 262144 else 4)
+                if N * M > 3e11:
+                    iters = 3
+                ms = ctx.time_loop(lambda k: gq_b200.quantize_rows(cbh, mu, std), iters, warm=2, bracket=False)
+                sweep.append({"n_samples": N, "rows": M, "ms": ms, "rows_per_s": M / (ms * 1e-3),
+                              "frac_of_tensor_peak_whole_call": 4.0 * GROUP * M * N / (ms * 1e-3) / 1e12 / pk["bf16_tflops"]})
+                del mu, std
+            cbh.close()
+            del cbn
+        out["configs[4]_sweep"] = {"workload": "quantize_rows (row prep + search + re-score), g = 16, D-trained rows, 1 GPU; at N > 1 GPUs the rows "
+                                               "split evenly (scaling_strong is the M = 1048576, N = 65536 point)", "points": sweep}
+    except Exception as e:  # noqa: BLE001
+        out["extras_error"] = repr(e)
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -180,6 +590,9 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=8192, help="rows per step of the CPU arm")
     ap.add_argument("--cpu-rows", type=int, default=8192, help="rows of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-extras", action="store_true", help="headline only (development runs)")
+    ap.add_argument("--sustain-s", type=float, default=3.0, help="length of the sustained loop in seconds (N = 1)")
+    ap.add_argument("--parity-rows", type=int, default=BATCH * HW * HW, help="timed rows re-checked against the oracle (N = 1)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -199,9 +612,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = pin_to_gpu_numa(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    ctx = Ctx(args, rank, world, local_rank)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -211,8 +626,8 @@ def main():
     M = B * HW * HW
     # input pool larger than the 126 MB L2: rotate so no step finds its latents cached
     z_bytes = B * 2 * CHANNELS * HW * HW * 4
-    pool_n = max(2, int(160e6 // z_bytes) + 1)
-    pool = [synth_latents(B, 17 * rank + i).to(dev) for i in range(pool_n)]
+    pool = pool_for(ctx, lambda i: synth_latents(B, 17 * rank + i), z_bytes)
+    pool_n = len(pool)
     host_pool = [synth_latents(B, 9000 + 17 * rank + i).pin_memory() for i in range(4)]
     torch.cuda.synchronize()
 
@@ -220,9 +635,7 @@ def main():
         zhat, info = reg(z)
         return zhat, info["indices"]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    barrier = ctx.barrier
 
     # ---- warm-up (also builds the prepared codebook and the workspace) ----
     for i in range(max(args.warmup, 3)):
@@ -309,47 +722,68 @@ def main():
 
     clocks = ClockSampler.window(sampler.stop(), t_epoch0, t_epoch1)
 
-    # ---- max over ranks ----
-    t = torch.tensor([total_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kern_ms_max = [float(x) for x in t.tolist()]
+    # ---- max over ranks; per-rank values kept ----
+    per_rank = ctx.gather_ranks(total_ms / args.steps, kern_ms, e2e_ms / e_steps, float(clocks["sm_mhz"] or 0.0))
+    total_ms, e2e_ms, kern_ms_max = ctx.max_over_ranks(total_ms, e2e_ms, kern_ms)
 
     ms_per_step = total_ms / args.steps
     value = world * M / (ms_per_step * 1e-3)
     e2e_value = world * M / (e2e_ms / e_steps * 1e-3)
 
-    pk = peaks()
+    pk = ctx.pk
     flops = 4.0 * GROUP * M * N_SAMPLES          # 64 flop per (row, codeword) pair
-    achieved = flops / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+    achieved = flops / (kern_ms_max * 1e-3) / 1e12 if kern_ms_max > 0 else 0.0
     peak = pk["bf16_tflops_sustained"] if total_ms > 2000 else pk["bf16_tflops"]
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "search_kernel_traffic.json")
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = "constant from " + tj.get("source", "profiles/search_kernel_traffic.json") + " (ncu --set full capture; not re-measured in this run)"
         except Exception:
             traffic = None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 search / f32 exact re-score", "data": "synthetic",
+        "dtype": "f16 operands, f16 tensor-core accumulators (search) / f32 exact re-score", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_samples": N_SAMPLES, "group": GROUP, "rows_per_gpu": M,
                    "global_batch": B * world, "latents": "D-trained (SURVEY 8d)", "parallelism": f"rows sharded by batch x{world}",
                    "l2": f"inputs rotate over a {pool_n}-batch pool ({pool_n * z_bytes / 1e6:.0f} MB > 126 MB L2); "
-                         "the 4 MB codebook image is L2-resident by design"},
+                         "the 4 MB codebook image is L2-resident by design",
+                   "host_numa_binding": numa},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": z_bytes, "d2h_bytes_per_step": idx_host[0].numel() * 8,
-                "note": "H2D on a copy stream, four input buffers in rotation; D2H of the indices on its own stream behind an event; the timed region ends after the last D2H"},
+                "note": "H2D on a copy stream, four input buffers in rotation; D2H of the int64 indices on its own stream behind an event; "
+                        "the timed region ends after the last D2H.  zhat (4 MB, = codebook[indices], reproducible on the host by a table "
+                        "lookup) and zhat_noquant stay on the device: the indices are the step's result a token pipeline reads back"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "quantize_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel_ms": kern_ms, "kernel_launches_timed": cnt.value,
-                     "algorithmic_flops_per_launch": flops, "peak_source": pk["source"] + (" (burst)" if peak == pk["bf16_tflops"] else " (sustained)")},
+        "roofline": {"bound": "tensor", "kernel": "quantize_tc_kernel (fp16 accumulators)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": kern_ms_max,
+                     "kernel_ms_note": "max over ranks of the mean library-side CUDA-event time per launch (launch gap of the bracketed launch included)",
+                     "kernel_launches_timed": cnt.value,
+                     "algorithmic_flops_per_launch": flops, "peak_source": pk["source"] + (" (burst)" if peak == pk["bf16_tflops"] else " (sustained)"),
+                     "whole_step_frac": flops / (ms_per_step * 1e-3) / 1e12 / peak},
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                    "samples": clocks["samples"]},
         "wall_s_timed_region": t_wall,
     }
+    if world > 1:
+        line["per_rank"] = {"ms_per_step": per_rank[0], "kernel_ms": per_rank[1], "e2e_ms_per_step": per_rank[2], "sm_mhz": per_rank[3],
+                            "note": "value / e2e / roofline use the max over ranks"}
+
+    extras_err = {}
+    if world > 1:
+        try:
+            line["exchange"] = leg_exchange(ctx, reg, pool)
+        except Exception as e:  # noqa: BLE001
+            extras_err["exchange"] = repr(e)
+    if not args.no_extras:
+        try:
+            line["scaling_strong"] = leg_strong(ctx, reg)
+        except Exception as e:  # noqa: BLE001
+            extras_err["scaling_strong"] = repr(e)
 
     if rank == 0 and world == 1 and args.cpu_rows > 0:
         import oracle
@@ -358,20 +792,52 @@ def main():
         cb, nlp = host_codebook(N_SAMPLES, GROUP)
         rows = args.cpu_rows
         # rows exactly as the module builds them on the device (so both sides see equal std / log std)
-        zz = pool[0].permute(0, 2, 3, 1).reshape(-1, 2 * CHANNELS)[:rows]
+        zz = pool[0].permute(0, 2, 3, 1).reshape(-1, 2 * CHANNELS)
         mu, lv = zz[:, :CHANNELS].contiguous(), zz[:, CHANNELS:].contiguous()
         std = torch.exp(0.5 * torch.clamp(lv, -30.0, 20.0))
-        a = (mu.cpu().numpy(), std.cpu().numpy(), std.log().cpu().numpy(), cb, nlp)
+        a_all = (mu.cpu().numpy(), std.cpu().numpy(), std.log().cpu().numpy())
+        a = tuple(x[:rows] for x in a_all)
         oracle.quantize(a[0][:256], a[1][:256], a[2][:256], cb, nlp, 1.0)
         t0 = time.perf_counter()
-        o_idx, _, _, _ = oracle.quantize(*a, 1.0)
+        o_idx, _, _, _ = oracle.quantize(*a, cb, nlp, 1.0)
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": rows / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-                                "sample": f"{rows} rows of pool[0] ({dt:.2f} s wall); rows are independent so the rate extrapolates"}
-        # parity of the very tensors that were timed
+        rate = rows / dt
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+                                "sample": f"{rows} rows of pool[0] ({dt:.2f} s wall); rows are independent so the rate extrapolates",
+                                "reference_torch_probe": TORCH_REFERENCE_PROBE}
+        # parity of the very tensors that were timed: as many rows as ~20 s of oracle time allow, the full batch on a 16-core host
+        prow = int(min(args.parity_rows, M, max(rows, rate * 20.0)))
+        if prow > rows:
+            o_idx, _, _, o_gap = oracle.quantize(*(x[:prow] for x in a_all), cb, nlp, 1.0)
+        else:
+            prow = rows
+            o_gap = None
         _, ind = step(pool[0])
-        got = ind.permute(0, 2, 3, 1).reshape(-1)[:rows].cpu().numpy()
-        line["parity"] = {"rows_checked": rows, "index_mismatches_vs_oracle": int((got != o_idx).sum())}
+        got = ind.permute(0, 2, 3, 1).reshape(-1)[:prow].cpu().numpy()
+        bad = got != o_idx
+        line["parity"] = {"rows_checked": prow, "rows_timed": M, "index_mismatches_vs_oracle": int(bad.sum()),
+                          "mismatch_rate": float(bad.mean()),
+                          "max_top2_gap_of_mismatches": (float(o_gap[bad].max()) if (o_gap is not None and bad.any()) else 0.0)}
+
+    if world == 1 and not args.no_extras:
+        try:
+            sampler2 = ClockSampler(local_rank)
+            sampler2.start()
+            time.sleep(0.3)
+            sus = leg_sustained(ctx, step, pool, flops, args.sustain_s)
+            w0, w1 = sus.pop("window")
+            sus["clocks"] = ClockSampler.window(sampler2.stop(), w0, w1)
+            line["sustained"] = sus
+        except Exception as e:  # noqa: BLE001
+            extras_err["sustained"] = repr(e)
+        try:
+            del pool
+            torch.cuda.empty_cache()
+            line["configs"] = leg_configs(ctx)
+        except Exception as e:  # noqa: BLE001
+            extras_err["configs"] = repr(e)
+    if extras_err:
+        line["extras_errors"] = extras_err
 
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -43,6 +43,9 @@ def _worker(rank, world, port, batch, out_dir):
     idx, _, _, _ = oracle.quantize(mu.numpy(), std.numpy(), std.log().numpy(), cb, nlp)
     local = torch.from_numpy(idx).reshape(hi - lo, l, 1)
     full = gd.all_gather_indices(local, batch)
+    packed = torch.from_numpy(oracle.pack_indices(idx, 1024).view(np.int16)).view(torch.uint16).reshape(hi - lo, l, 1)
+    full_packed = gd.all_gather_indices(packed, batch)          # the uint16 wire format travels as bytes
+    assert full_packed.dtype == torch.uint16
     # KL partials
     r = oracle.kl(zs.numpy(), g, 10, 0.5, 1.3, 0.7, 2.0)
     kl2 = r["kl2"].astype(np.float64)
@@ -57,6 +60,7 @@ def _worker(rank, world, port, batch, out_dir):
         want, _, _, _ = oracle.quantize(mu_a.numpy(), std_a.numpy(), std_a.log().numpy(), cb, nlp)
         ra = oracle.kl(z.numpy(), g, 10, 0.5, 1.3, 0.7, 2.0)
         np.savez(os.path.join(out_dir, "r0.npz"), full=full.numpy(), want=want.reshape(batch, l, 1), glob=glob.numpy(),
+                 full_packed=full_packed.view(torch.int16).numpy().view(np.uint16).astype(np.int64),
                  hist=hist.numpy(), hist_want=oracle.index_histogram(want, 1024),
                  ref=np.array([ra["kl_loss"], ra["bits_mean"], ra["bits_min"], ra["bits_max"]]))
     dist.barrier()
@@ -69,6 +73,7 @@ def test_sharded_rows_match_single_process(tmp_path, batch):
     mp.spawn(_worker, args=(world, _free_port(), batch, str(tmp_path)), nprocs=world, join=True)
     r = np.load(tmp_path / "r0.npz")
     assert np.array_equal(r["full"], r["want"])
+    assert np.array_equal(r["full_packed"], r["want"])
     np.testing.assert_allclose(r["glob"], r["ref"], rtol=1e-5)
     assert np.array_equal(r["hist"], r["hist_want"]) and r["hist"].sum() == batch * 16
 

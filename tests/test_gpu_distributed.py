@@ -1,0 +1,74 @@
+"""2-rank NCCL test of the row-sharded path on GPUs (skipped on boxes with fewer than two):
+every rank runs the CUDA quantizer / KL kernel on its batch shard, the NCCL exchanges of
+gq_b200.distributed must reproduce what one process computes on the whole batch
+(the reference's pattern: per-rank result -> all_gather, eval.py:167-201)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, batch, out_dir):
+    for p in (str(ROOT), str(ROOT / "vq-vae-from-gaussian-vae_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import gq_b200
+    from gq_b200 import distributed as gd
+    from gq_b200.ops import GQ_LAYOUT_BLC
+    n_samples, l, C, g = 4096, 64, 16, 16
+    gen = torch.Generator().manual_seed(0)
+    z = torch.cat([torch.randn(batch, l, C, generator=gen) * 0.8, -1.4 + 0.3 * torch.randn(batch, l, C, generator=gen)], 2).to(dev)
+    reg = gq_b200.GaussianQuantRegularizer(format="blc", n_samples=n_samples, group=g, backend="cuda").to(dev).eval()
+    zs = gd.shard_batch(z)
+    _, info = reg(zs)
+    full = gd.all_gather_indices(info["indices"], batch)                       # int64 over NCCL
+    full_p = gd.all_gather_indices(reg.pack_indices(info["indices"]), batch)   # packed uint16 over NCCL
+    hist = gd.global_usage_histogram(reg.accumulate_usage(info["indices"]))
+    # train branch: rank-local KL partials -> one collective -> the unsharded batch's statistics
+    eps = torch.zeros(zs.shape[0], l, C, device=dev)
+    _, _, st = gq_b200.kl_penalty(zs, eps, g, GQ_LAYOUT_BLC, target_bits=12.0, lam=1.3, lam_min=0.7, lam_max=2.0)
+    glob = gd.global_kl_stats(st, zs.shape[0] * l, batch, 1.3)
+    if rank == 0:
+        _, info_all = reg(z)                                                    # one process, whole batch
+        _, kl_all, st_all = gq_b200.kl_penalty(z, torch.zeros(batch, l, C, device=dev), g, GQ_LAYOUT_BLC, target_bits=12.0,
+                                               lam=1.3, lam_min=0.7, lam_max=2.0)
+        np.savez(os.path.join(out_dir, "r0.npz"), full=full.cpu().numpy(), want=info_all["indices"].cpu().numpy(),
+                 full_p=reg.unpack_indices(full_p).cpu().numpy(), packed_dtype=str(full_p.dtype),
+                 hist=hist.cpu().numpy(), hist_want=reg.accumulate_usage(info_all["indices"]).cpu().numpy(),
+                 glob=glob.cpu().numpy(), ref=st_all[:4].cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [8, 5])     # even and ragged split
+def test_nccl_sharded_rows_match_single_process(tmp_path, batch):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), batch, str(tmp_path)), nprocs=world, join=True)
+    r = np.load(tmp_path / "r0.npz")
+    assert np.array_equal(r["full"], r["want"])              # all-gathered shard indices == single-process indices
+    assert np.array_equal(r["full_p"], r["want"]) and str(r["packed_dtype"]) == "torch.uint16"
+    assert np.array_equal(r["hist"], r["hist_want"])
+    np.testing.assert_allclose(r["glob"], r["ref"], rtol=1e-5)

@@ -78,6 +78,13 @@ __device__ __forceinline__ float score_exact(const float (&x)[G], const float (&
     return sum_torch_inner<G>(t);
 }
 
+// torch.clamp(x, lo, hi): NaN propagates (fminf / fmaxf would silently return the bound, turning a NaN from the
+// encoder's logvar head into a finite loss, zhat and gradient; the reference yields NaN, which trainers detect)
+__device__ __forceinline__ float clamp_torch(float x, float lo, float hi)
+{
+    return (x != x) ? x : fminf(fmaxf(x, lo), hi);
+}
+
 template <int G>
 __device__ __forceinline__ void load_row(const float *__restrict__ p, float (&v)[G])
 {

@@ -157,7 +157,7 @@ kl_fwd_kernel(const float *__restrict__ z, const float *__restrict__ eps, float 
         float zh[G];
 #pragma unroll
         for (int k = 0; k < G; ++k) {
-            float v = fminf(fmaxf(lv[k], lv_lo), lv_hi);
+            float v = clamp_torch(lv[k], lv_lo, lv_hi);
             float var = expf(v);
             float sd = expf(0.5f * v);
             float e = mu[k] * mu[k] + var;
@@ -231,12 +231,12 @@ kl_bwd_kernel(const float *__restrict__ z, const float *__restrict__ eps, const 
         for (int k = 0; k < G; ++k) {
             const float e = eps ? ep[k] : 0.f;
             const float g_ = grad_zhat ? gz[k] : 0.f;
-            const float v = fminf(fmaxf(lr[k], lv_lo), lv_hi);
+            const float v = clamp_torch(lr[k], lv_lo, lv_hi);
             const bool inside = (lr[k] >= lv_lo) && (lr[k] <= lv_hi);
             const float var = expf(v);
             const float sd = expf(0.5f * v);
             gmu[k] = s * (2.0f * kKlScale) * mu[k] + g_;
-            glv[k] = inside ? (s * kKlScale * (var - 1.0f) + g_ * e * 0.5f * sd) : 0.f;
+            glv[k] = inside ? (s * kKlScale * (var - 1.0f) + g_ * e * 0.5f * sd) : (lr[k] != lr[k] ? lr[k] : 0.f);   // clamp backward: grad * mask, and NaN * 0 = NaN as in torch
         }
         if (vec) {
 #pragma unroll
@@ -295,7 +295,7 @@ kl_fwd_blc16_kernel(const float *__restrict__ z, const float *__restrict__ eps, 
         float sl[4], zh[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float v = fminf(fmaxf(lr[k], lv_lo), lv_hi);
+            const float v = clamp_torch(lr[k], lv_lo, lv_hi);
             const float var = expf(v);
             const float sd = expf(0.5f * v);
             float e = mu[k] * mu[k] + var;
@@ -359,12 +359,12 @@ kl_bwd_blc16_kernel(const float *__restrict__ z, const float *__restrict__ eps, 
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float s = sc * wg[k];
-            const float v = fminf(fmaxf(lr[k], lv_lo), lv_hi);
+            const float v = clamp_torch(lr[k], lv_lo, lv_hi);
             const bool inside = (lr[k] >= lv_lo) && (lr[k] <= lv_hi);
             const float var = expf(v);
             const float sd = expf(0.5f * v);
             gmu[k] = s * (2.0f * kKlScale) * mu[k] + gz[k];
-            glv[k] = inside ? (s * kKlScale * (var - 1.0f) + gz[k] * ep[k] * 0.5f * sd) : 0.f;
+            glv[k] = inside ? (s * kKlScale * (var - 1.0f) + gz[k] * ep[k] * 0.5f * sd) : (lr[k] != lr[k] ? lr[k] : 0.f);   // clamp backward: grad * mask, and NaN * 0 = NaN as in torch
         }
         reinterpret_cast<float4 *>(grad_z + tok * 32)[q] = make_float4(gmu[0], gmu[1], gmu[2], gmu[3]);
         reinterpret_cast<float4 *>(grad_z + tok * 32 + 16)[q] = make_float4(glv[0], glv[1], glv[2], glv[3]);
@@ -412,7 +412,7 @@ kl_fwd_bchw16_kernel(const float *__restrict__ z, const float *__restrict__ eps,
             float zh[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const float v = fminf(fmaxf(lr[t], lv_lo), lv_hi);
+                const float v = clamp_torch(lr[t], lv_lo, lv_hi);
                 const float var = expf(v);
                 const float sd = expf(0.5f * v);
                 float e = mu[t] * mu[t] + var;
@@ -491,12 +491,12 @@ kl_bwd_bchw4_kernel(const float *__restrict__ z, const float *__restrict__ eps, 
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const float s = sc * wg[t];
-            const float v = fminf(fmaxf(lr[t], lv_lo), lv_hi);
+            const float v = clamp_torch(lr[t], lv_lo, lv_hi);
             const bool inside = (lr[t] >= lv_lo) && (lr[t] <= lv_hi);
             const float var = expf(v);
             const float sd = expf(0.5f * v);
             gmu[t] = s * (2.0f * kKlScale) * mu[t] + gz[t];
-            glv[t] = inside ? (s * kKlScale * (var - 1.0f) + gz[t] * en[t] * 0.5f * sd) : 0.f;
+            glv[t] = inside ? (s * kKlScale * (var - 1.0f) + gz[t] * en[t] * 0.5f * sd) : (lr[t] != lr[t] ? lr[t] : 0.f);   // clamp backward: grad * mask, and NaN * 0 = NaN as in torch
         }
         reinterpret_cast<float4 *>(grad_z + (bi * 2 * C + c) * l)[t4] = make_float4(gmu[0], gmu[1], gmu[2], gmu[3]);
         reinterpret_cast<float4 *>(grad_z + (bi * 2 * C + C + c) * l)[t4] = make_float4(glv[0], glv[1], glv[2], glv[3]);

@@ -1657,7 +1657,7 @@ frontend_kernel(const float *__restrict__ z, const float *__restrict__ eps, cons
 #pragma unroll
         for (int k = 0; k < G; ++k) {
             m[k] = __ldg(z + zb + k * zs);
-            const float lv = fminf(fmaxf(__ldg(z + zb + lvo + k * zs), lv_lo), lv_hi);
+            const float lv = clamp_torch(__ldg(z + zb + lvo + k * zs), lv_lo, lv_hi);
             s[k] = expf(__fmul_rn(0.5f, lv));
             ls[k] = logf(s[k]);
             if (zhat_nq) zhat_nq[eb + k * es] = __fadd_rn(m[k], __fmul_rn(__ldg(eps + eb + k * es), s[k]));

@@ -7,10 +7,12 @@ the regularizer's lambda controller sees rank-local statistics, gaussian.py:89,1
 data path needs no collective.  Two optional exchanges are provided for callers that want the
 single-process result on every rank:
 
-  all_gather_indices   NCCL all_gather of the int64 index shards (<= 1 MB per rank at 1 M rows)
-  global_kl_stats      SUM / MIN / MAX all_reduce of the four KL partials, so that kl_loss and
-                       bits-* equal the unsharded batch (a deliberate improvement over the
-                       reference's rank-local lambda controller; rank-local stays the default)
+  all_gather_indices   one NCCL all_gather_into_tensor of the index shards, int64 or the packed
+                       uint16 / int32 stream (<= 1 MB resp. 256 KB per rank at 1 M rows)
+  global_kl_stats      ONE all_gather of five float64 per rank (sum kl2, sum w*kl2, count, min, max),
+                       folded locally, so that kl_loss and bits-* equal the unsharded batch (a
+                       deliberate improvement over the reference's rank-local lambda controller;
+                       rank-local stays the default)
 
 Everything here works on whatever backend the process group uses (nccl on GPUs, gloo in the
 CPU tests); nothing in this file touches the CUDA library.
@@ -42,7 +44,10 @@ def shard_batch(x: torch.Tensor, rank: Optional[int] = None, world: Optional[int
 
 def all_gather_indices(local: torch.Tensor, global_batch: int, group=None) -> torch.Tensor:
     """Concatenate per-rank index shards along dim 0 into the [global_batch, ...] tensor every
-    rank would have produced alone.  Shards may be ragged (global_batch % world != 0)."""
+    rank would have produced alone (the pattern of eval.py:167-201: per-rank result -> all_gather).
+    Works on int64 indices and on the packed uint16 / int32 stream of `pack_indices` (a quarter of
+    the bytes on the wire).  Even splits are ONE `all_gather_into_tensor` straight into the result;
+    ragged splits (global_batch % world != 0) pad to the largest shard."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     sizes = [shard_bounds(global_batch, r, world) for r in range(world)]
@@ -50,31 +55,45 @@ def all_gather_indices(local: torch.Tensor, global_batch: int, group=None) -> to
     lo, hi = sizes[rank]
     if local.shape[0] != hi - lo:
         raise RuntimeError(f"rank {rank}: shard has {local.shape[0]} items, expected {hi - lo}")
-    pad = local
-    if local.shape[0] < mx:
-        pad = torch.cat([local, local.new_zeros((mx - local.shape[0],) + tuple(local.shape[1:]))], 0)
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad.contiguous(), group=group)
-    return torch.cat([b[: h - l] for b, (l, h) in zip(bufs, sizes)], 0)
+    local = local.contiguous()
+    # neither NCCL nor gloo has a 16-bit integer type: ship the packed stream as its bytes
+    wire = local.view(torch.uint8) if local.dtype == torch.uint16 else local
+    if global_batch % world == 0:
+        out = torch.empty((global_batch,) + tuple(wire.shape[1:]), dtype=wire.dtype, device=wire.device)
+        dist.all_gather_into_tensor(out, wire, group=group)
+    else:
+        pad = wire
+        if wire.shape[0] < mx:
+            pad = torch.cat([wire, wire.new_zeros((mx - wire.shape[0],) + tuple(wire.shape[1:]))], 0)
+        buf = torch.empty((world * mx,) + tuple(wire.shape[1:]), dtype=wire.dtype, device=wire.device)
+        dist.all_gather_into_tensor(buf, pad.contiguous(), group=group)
+        out = torch.cat([buf[r * mx: r * mx + (h - l)] for r, (l, h) in enumerate(sizes)], 0)
+    return out.view(torch.uint16) if local.dtype == torch.uint16 else out
 
 
 def global_kl_stats(stats: torch.Tensor, local_groups: int, global_batch: int, lam: float, group=None) -> torch.Tensor:
-    """Turn rank-local gq_kl_fwd stats into the unsharded batch's.
+    """Turn rank-local gq_kl_fwd stats into the unsharded batch's with ONE collective.
 
     stats (float32[8]) = [kl_loss, bits_mean, bits_min, bits_max, sum_kl2, sum_w_kl2, 0, 0];
     returns a new float32[4] = [kl_loss, bits_mean, bits_min, bits_max] over all ranks:
-    kl_loss = lam * sum_all(w*kl2) / global_batch (gaussian.py:96-98)."""
-    sums = torch.stack([stats[4].double(), stats[5].double(), torch.tensor(float(local_groups), dtype=torch.float64, device=stats.device)])
-    mn = stats[2].clone()
-    mx = stats[3].clone()
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    kl_loss = lam * sum_all(w*kl2) / global_batch (gaussian.py:96-98).  Every rank contributes the
+    five numbers [sum_kl2, sum_w_kl2, groups, min, max] as float64 to a single all_gather (40 bytes per
+    rank: latency-bound, one launch) and folds the world-size rows locally in rank order, so every rank
+    gets the same bits."""
+    world = dist.get_world_size(group)
+    mine = torch.empty(5, dtype=torch.float64, device=stats.device)
+    mine[0:2] = stats[4:6].double()
+    mine[2] = float(local_groups)
+    mine[3:5] = stats[2:4].double()
+    allv = torch.empty(world * 5, dtype=torch.float64, device=stats.device)
+    dist.all_gather_into_tensor(allv, mine, group=group)
+    allv = allv.view(world, 5)
+    sums = allv[:, 0:3].sum(0)
     out = torch.empty(4, dtype=torch.float32, device=stats.device)
     out[0] = (lam * sums[1] / float(global_batch)).float()
     out[1] = (sums[0] / sums[2]).float()
-    out[2] = mn
-    out[3] = mx
+    out[2] = allv[:, 3].min().float()
+    out[3] = allv[:, 4].max().float()
     return out
 
 

@@ -3,7 +3,10 @@
 PyTorch is plumbing here: it owns device memory and the current stream; every operator
 below validates its tensors the way the reference wrapper does
 (gq_cuda_extension/gq_cuda/csrc/cuda/gq_cuda.cu:91-101), then hands raw device pointers to
-the C entry point on `torch.cuda.current_stream()`.  Nothing synchronises.
+the C entry point on `torch.cuda.current_stream()`.  Nothing synchronises unless a caller opts into
+`check_range=True` (dequant / pack_indices / index_histogram then read an error flag back, one blocking D2H).
+A `Codebook` caches one scratch workspace and its device-side counters: use a handle (and the module that
+owns it) from one stream at a time.
 """
 from __future__ import annotations
 

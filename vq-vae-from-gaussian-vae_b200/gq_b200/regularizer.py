@@ -57,6 +57,34 @@ class _GQBase(nn.Module):
         self._cb: Optional[Codebook] = None
         self._cb_key = None
 
+    # The prepared device codebook is a native handle (ctypes pointer): it cannot be pickled or deep-copied, and two
+    # modules must never own one handle (its finaliser frees device memory).  Copies therefore drop it and
+    # rebuild it lazily on their first eval forward / dequant -- the reference module can be deep-copied (EMA
+    # copies) and pickled (torch.save(model)) at any time, and so can this one.
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_cb"] = None
+        state["_cb_key"] = None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k in ("_cb", "_cb_key") else copy.deepcopy(v, memo)
+        return new
+
+    #: opt-in range check of index tensors in dequant / pack_indices / accumulate_usage: reading the flag back is a
+    #: blocking device-to-host sync, which the reference's index_select never does (gaussian.py:171-173; on a GPU it
+    #: raises a device-side assert asynchronously).  Off: out-of-range ids read codeword 0.  Also GQ_B200_CHECK_RANGE=1.
+    check_range = False
+
+    def _check_range(self) -> bool:
+        import os
+        return bool(self.check_range) or os.environ.get("GQ_B200_CHECK_RANGE", "0") == "1"
+
     def _codebook(self) -> Codebook:
         ps = self.prior_samples
         if not ps.is_cuda:
@@ -226,19 +254,19 @@ class GaussianQuantRegularizer(_GQBase):
     def dequant(self, indices):
         """gaussian.py:162-178.  Also accepts the packed stream of `pack_indices` (uint16 / int32)."""
         layout = GQ_LAYOUT_BCHW if self.format == "bchw" else GQ_LAYOUT_BLC
-        return ops.dequant(self._codebook(), indices, layout, check_range=True)
+        return ops.dequant(self._codebook(), indices, layout, check_range=self._check_range())
 
     # ---- not in the reference module: the index stream after the quantizer (SURVEY 8f ranks 3-4) ----
     def pack_indices(self, indices):
         """int64 indices -> uint16 (n_samples <= 65536) / int32, same shape; `dequant` reads either."""
-        return ops.pack_indices(indices, self.n_samples, check_range=True)
+        return ops.pack_indices(indices, self.n_samples, check_range=self._check_range())
 
     def unpack_indices(self, packed):
         return ops.unpack_indices(packed, self.n_samples)
 
     def accumulate_usage(self, indices, hist=None):
         """all_hist += histogram(indices) over the codebook (eval.py:127,152-154); returns the int64 histogram."""
-        return ops.index_histogram(indices, self.n_samples, hist, check_range=True)
+        return ops.index_histogram(indices, self.n_samples, hist, check_range=self._check_range())
 
     @staticmethod
     def codebook_usage(hist):
@@ -272,7 +300,7 @@ class GaussianQuantRegularizer2(_GQBase):
         self.backend = backend
 
     def quant_gaussian(self, z):
-        z = torch.movedim(z, self.dim_idx, -1)
+        z = torch.movedim(z.float(), self.dim_idx, -1)   # the kernels are fp32 (as GQ v1's z.float()); outputs are fp32
         assert z.shape[-1] % (self.dim * 2) == 0
         z_shape = z.shape
         z2 = z.reshape(-1, z_shape[-1])
@@ -319,7 +347,7 @@ class GaussianQuantRegularizer2(_GQBase):
     def quant_vq(self, z):
         if self.backend not in ("cuda", "torch"):
             raise ValueError
-        z = torch.movedim(z, self.dim_idx, -1)
+        z = torch.movedim(z.float(), self.dim_idx, -1)
         assert z.shape[-1] % (self.dim * 2) == 0
         z_shape = z.shape
         z2 = z.reshape(-1, z_shape[-1])
@@ -354,6 +382,6 @@ class GaussianQuantRegularizer2(_GQBase):
         i_shape = indices.shape
         codebook_num = i_shape[-1]
         flat = indices.reshape(1, -1, 1).contiguous()
-        zhat = ops.dequant(self._codebook(), flat, GQ_LAYOUT_BLC, check_range=True)
+        zhat = ops.dequant(self._codebook(), flat, GQ_LAYOUT_BLC, check_range=self._check_range())
         zhat = zhat.reshape(-1, codebook_num * self.dim).reshape(*i_shape[:-1], -1)
         return torch.movedim(zhat, -1, self.dim_idx)
