@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define GQ_B200_ABI_VERSION 2
+#define GQ_B200_ABI_VERSION 3
 
 typedef void *gq_stream_t; /* cudaStream_t */
 
@@ -167,6 +167,14 @@ int gq_kl_fwd(const float *z, const float *eps, float *zhat, float *w_out, float
 int gq_kl_bwd(const float *z, const float *eps, const float *w, const float *grad_zhat,
               const float *grad_kl, float *grad_z, int64_t b, int64_t l, int C, int g,
               int layout, float lv_lo, float lv_hi, float lam, gq_stream_t stream);
+
+/* Fold the gq_kl_fwd statistics of `world` row shards (all_stats: world x 8 floats, the out_stats of every rank
+ * as an all-gather delivers them) into the unsharded batch's [kl_loss, bits_mean, bits_min, bits_max] -> out4:
+ * kl_loss = lam * sum(w*kl2) / global_batch, bits_mean = sum(kl2) / total_groups (gaussian.py:89-98 over the
+ * global batch), sums in double in rank order (every rank computes the same bits).  One tiny kernel: with the
+ * all-gather it is the whole KL exchange of a sharded training step. */
+int gq_kl_fold(const float *all_stats, int world, double lam, double global_batch, double total_groups,
+               float *out4, gq_stream_t stream);
 
 /* ---- measurement and diagnostics (no reference counterpart) ------------------------------
  * gq_profile_enable(n): every n-th later gq_quantize (n = 1: every one; 0: off) records a CUDA-event pair around its search

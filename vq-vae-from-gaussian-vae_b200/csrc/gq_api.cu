@@ -324,4 +324,11 @@ int gq_kl_bwd(const float *z, const float *eps, const float *w, const float *gra
                          (cudaStream_t)stream);
 }
 
+int gq_kl_fold(const float *all_stats, int world, double lam, double global_batch, double total_groups, float *out4,
+               gq_stream_t stream)
+{
+    if (!all_stats || !out4 || world <= 0 || !(global_batch > 0.0) || !(total_groups > 0.0)) { set_error("gq_kl_fold: bad argument"); return GQ_ERR_INVALID; }
+    return launch_kl_fold(all_stats, world, lam, global_batch, total_groups, out4, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -60,6 +60,9 @@ int launch_kl_bwd(const float *z, const float *eps, const float *w, const float 
                   const float *grad_kl, float *grad_z, int64_t b, int64_t l, int C, int g, int layout,
                   float lv_lo, float lv_hi, float lam, cudaStream_t stream);
 
+int launch_kl_fold(const float *all_stats, int world, double lam, double global_batch, double total_groups, float *out4,
+                   cudaStream_t stream);
+
 int device_sm_count();
 int device_cc_major();
 

@@ -604,4 +604,37 @@ int launch_kl_bwd(const float *z, const float *eps, const float *w, const float 
     return check_launch("kl_bwd_kernel");
 }
 
+// Fold per-rank statistics (world x [kl_loss, bits_mean, bits_min, bits_max, sum_kl2, sum_w_kl2, -, -]) into the
+// global batch's four scalars; sums in double, in rank order.  fminf / fmaxf skip NaN, so a NaN minimum or maximum of
+// one shard is carried over explicitly (torch.min / max propagate it).
+__global__ void kl_fold_kernel(const float *__restrict__ all_stats, int world, double lam, double global_batch,
+                               double total_groups, float *__restrict__ out4)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s_kl2 = 0.0, s_wkl2 = 0.0;
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    bool nan_mn = false, nan_mx = false;
+    for (int r = 0; r < world; ++r) {
+        const float *st = all_stats + 8 * r;
+        s_kl2 += (double)st[4];
+        s_wkl2 += (double)st[5];
+        nan_mn |= st[2] != st[2];
+        nan_mx |= st[3] != st[3];
+        mn = fminf(mn, st[2]);
+        mx = fmaxf(mx, st[3]);
+    }
+    out4[0] = (float)(lam * s_wkl2 / global_batch);
+    out4[1] = (float)(s_kl2 / total_groups);
+    out4[2] = nan_mn ? CUDART_NAN_F : mn;
+    out4[3] = nan_mx ? CUDART_NAN_F : mx;
+}
+
+int launch_kl_fold(const float *all_stats, int world, double lam, double global_batch, double total_groups, float *out4,
+                   cudaStream_t stream)
+{
+    kl_fold_kernel<<<1, 32, 0, stream>>>(all_stats, world, lam, global_batch, total_groups, out4);
+    count_launch();
+    return check_launch("kl_fold_kernel");
+}
+
 }  // namespace gq

@@ -19,7 +19,7 @@ GQ_OK = 0
 GQ_LAYOUT_BLC = 0
 GQ_LAYOUT_BCHW = 1
 GQ_MODE_AUTO, GQ_MODE_FAST, GQ_MODE_ROBUST = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); mirrors include/gq_b200.h one to one
 PROTOTYPES = {
@@ -59,6 +59,7 @@ PROTOTYPES = {
                           c_void_p, c_int64, c_void_p]),
     "gq_kl_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                           c_int64, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
+    "gq_kl_fold": (c_int, [c_void_p, c_int, c_double, c_double, c_double, c_void_p, c_void_p]),
     # measurement / diagnostics (no reference counterpart)
     "gq_profile_enable": (None, [c_int]),
     "gq_profile_read": (c_int, [POINTER(c_double), POINTER(c_int)]),

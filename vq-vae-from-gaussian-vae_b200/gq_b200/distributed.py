@@ -9,13 +9,13 @@ single-process result on every rank:
 
   all_gather_indices   one NCCL all_gather_into_tensor of the index shards, int64 or the packed
                        uint16 / int32 stream (<= 1 MB resp. 256 KB per rank at 1 M rows)
-  global_kl_stats      ONE all_gather of five float64 per rank (sum kl2, sum w*kl2, count, min, max),
-                       folded locally, so that kl_loss and bits-* equal the unsharded batch (a
+  global_kl_stats      ONE all_gather of the eight gq_kl_fwd statistics per rank (32 bytes) + ONE fold kernel
+                       (gq_kl_fold), so that kl_loss and bits-* equal the unsharded batch (a
                        deliberate improvement over the reference's rank-local lambda controller;
                        rank-local stays the default)
 
 Everything here works on whatever backend the process group uses (nccl on GPUs, gloo in the
-CPU tests); nothing in this file touches the CUDA library.
+CPU tests); only global_kl_stats on CUDA tensors calls into the CUDA library (its one-kernel fold).
 """
 from __future__ import annotations
 
@@ -71,29 +71,37 @@ def all_gather_indices(local: torch.Tensor, global_batch: int, group=None) -> to
     return out.view(torch.uint16) if local.dtype == torch.uint16 else out
 
 
-def global_kl_stats(stats: torch.Tensor, local_groups: int, global_batch: int, lam: float, group=None) -> torch.Tensor:
-    """Turn rank-local gq_kl_fwd stats into the unsharded batch's with ONE collective.
+def global_kl_stats(stats: torch.Tensor, local_groups: int, global_batch: int, lam: float, group=None,
+                    total_groups: Optional[int] = None) -> torch.Tensor:
+    """Turn rank-local gq_kl_fwd stats into the unsharded batch's: ONE collective + ONE kernel.
 
     stats (float32[8]) = [kl_loss, bits_mean, bits_min, bits_max, sum_kl2, sum_w_kl2, 0, 0];
     returns a new float32[4] = [kl_loss, bits_mean, bits_min, bits_max] over all ranks:
-    kl_loss = lam * sum_all(w*kl2) / global_batch (gaussian.py:96-98).  Every rank contributes the
-    five numbers [sum_kl2, sum_w_kl2, groups, min, max] as float64 to a single all_gather (40 bytes per
-    rank: latency-bound, one launch) and folds the world-size rows locally in rank order, so every rank
-    gets the same bits."""
+    kl_loss = lam * sum_all(w*kl2) / global_batch (gaussian.py:96-98).  Every rank contributes its eight floats
+    to a single all_gather (32 bytes per rank: latency-bound) and folds the world-size rows with gq_kl_fold
+    (sums in double, rank order: every rank gets the same bits).  `total_groups` is the number of KL groups of
+    the whole batch (global_batch * tokens * sub-codebooks); when None it is taken as local_groups scaled by
+    global_batch over this rank's share, which is exact because every image contributes the same number."""
     world = dist.get_world_size(group)
-    mine = torch.empty(5, dtype=torch.float64, device=stats.device)
-    mine[0:2] = stats[4:6].double()
-    mine[2] = float(local_groups)
-    mine[3:5] = stats[2:4].double()
-    allv = torch.empty(world * 5, dtype=torch.float64, device=stats.device)
-    dist.all_gather_into_tensor(allv, mine, group=group)
-    allv = allv.view(world, 5)
-    sums = allv[:, 0:3].sum(0)
+    rank = dist.get_rank(group)
+    if total_groups is None:
+        lo, hi = shard_bounds(global_batch, rank, world)
+        total_groups = local_groups // max(hi - lo, 1) * global_batch
+    allv = torch.empty(world * 8, dtype=torch.float32, device=stats.device)
+    dist.all_gather_into_tensor(allv, stats.contiguous(), group=group)
     out = torch.empty(4, dtype=torch.float32, device=stats.device)
-    out[0] = (lam * sums[1] / float(global_batch)).float()
-    out[1] = (sums[0] / sums[2]).float()
-    out[2] = allv[:, 3].min().float()
-    out[3] = allv[:, 4].max().float()
+    if stats.is_cuda:
+        from . import _lib
+        with torch.cuda.device(stats.device):
+            _lib.check(_lib.lib().gq_kl_fold(allv.data_ptr(), world, float(lam), float(global_batch), float(total_groups),
+                                             out.data_ptr(), torch.cuda.current_stream().cuda_stream), "gq_kl_fold")
+        return out
+    # host tensors (the gloo tests of this module's logic): the same fold in torch
+    a = allv.view(world, 8).double()
+    out[0] = (lam * a[:, 5].sum() / float(global_batch)).float()
+    out[1] = (a[:, 4].sum() / float(total_groups)).float()
+    out[2] = a[:, 2].min().float()
+    out[3] = a[:, 3].max().float()
     return out
 
 
