@@ -182,7 +182,8 @@ int gq_kl_fold(const float *all_stats, int world, double lam, double global_batc
  * recorded events).  gq_set_window_max: rows whose rigorous error window exceeds `w` (32 `w` with the split-precision image; score
  * units) go to the exact scan (default 3.0).  gq_debug_tc_scores dumps the raw tensor-core
  * score matrix [M_pad, n_pad] and the scaled per-row windows [M_pad]; gq_debug_plan returns
- * the stream-K decomposition {units, tiles, ctas, steps_per_cta, nseg, M_pad}. */
+ * the stream-K decomposition {units, tiles, ctas, steps_per_cta, nseg, M_pad, unit_rows, tile_cols} of the fp32-accumulator
+ * kernel (acc16 = 0: 256-row units, 128-codeword tiles) or the fp16-accumulator kernel (1: 128-row units, 256-codeword tiles). */
 void gq_profile_enable(int on);
 int gq_profile_read(double *total_ms, int *count);
 void gq_set_window_max(float w);
@@ -192,7 +193,7 @@ void gq_set_chained_launch(int on);
 int gq_debug_tc_scores(const gq_codebook_t *cb, const float *mu, const float *std,
                        const float *log_std, int64_t M, void *workspace, int64_t workspace_bytes,
                        float *dump, float *wrow_out, gq_stream_t stream);
-void gq_debug_plan(int64_t N, int64_t M, int sms, int64_t *out);
+void gq_debug_plan(int64_t N, int64_t M, int sms, int acc16, int64_t *out);
 
 #ifdef __cplusplus
 }

@@ -46,11 +46,11 @@ def stage_dump(N, g, M):
     mu, std, lstd = make_rows(M, g, "trained")
     cb = gq_b200.Codebook(cbh.cuda(), None, 1.0)
     L = _lib.lib()
-    L.gq_debug_plan.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
-    plan = (ctypes.c_int64 * 6)()
-    L.gq_debug_plan(N, M, 148, plan)
-    units, tiles, ctas, spc, nseg, M_pad = list(plan)
-    n_pad = tiles * 128
+    L.gq_debug_plan.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    plan = (ctypes.c_int64 * 8)()
+    L.gq_debug_plan(N, M, 148, 1 if g in (8, 16) else 0, plan)
+    units, tiles, ctas, spc, nseg, M_pad, unit_rows, tile_cols = list(plan)
+    n_pad = tiles * tile_cols
     ws = cb.workspace(M)
     dump = torch.full((M_pad, n_pad), float("nan"), device="cuda")
     wrow = torch.zeros(M_pad, device="cuda")

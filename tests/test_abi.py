@@ -89,12 +89,14 @@ def pieces_of(cta, tiles, spc, total):
 @pytest.mark.parametrize("N,M", [(65536, 65536), (65536, 1024), (65536, 1), (4096, 300), (1000, 7), (262144, 4096),
                                  (65536, 1048576), (4096, 257), (128, 256), (65536, 37 * 256 + 5)])
 @pytest.mark.parametrize("sms", [148, 132, 1])
-def test_streamk_plan_covers_every_step_once(lib, N, M, sms):
-    lib.gq_debug_plan.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
-    out = (ctypes.c_int64 * 6)()
-    lib.gq_debug_plan(N, M, sms, out)
-    units, tiles, ctas, spc, nseg, m_pad = list(out)
-    assert units == -(-M // 256) and m_pad == units * 256 and tiles == -(-N // 128)
+@pytest.mark.parametrize("acc16", [0, 1], ids=["fp32acc-256x128", "fp16acc-128x256"])
+def test_streamk_plan_covers_every_step_once(lib, N, M, sms, acc16):
+    lib.gq_debug_plan.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
+    out = (ctypes.c_int64 * 8)()
+    lib.gq_debug_plan(N, M, sms, acc16, out)
+    units, tiles, ctas, spc, nseg, m_pad, unit_rows, tile_cols = list(out)
+    assert (unit_rows, tile_cols) == ((128, 256) if acc16 else (256, 128))
+    assert m_pad == -(-M // 256) * 256 and units == m_pad // unit_rows and tiles == -(-N // tile_cols)
     assert 1 <= ctas <= sms
     total = units * tiles
     assert (ctas - 1) * spc < total <= ctas * spc

@@ -81,7 +81,7 @@ int gq_debug_tc_scores(const gq_codebook_t *cb, const float *mu, const float *st
     if (!cb || !mu || !std || !dump || !wrow_out || M <= 0) { set_error("gq_debug_tc_scores: bad argument"); return GQ_ERR_INVALID; }
     return debug_tc_scores(cb, mu, std, log_std, M, workspace, workspace_bytes, dump, wrow_out, (cudaStream_t)stream);
 }
-void gq_debug_plan(int64_t N, int64_t M, int sms, int64_t *out) { debug_plan(N, M, sms, out); }
+void gq_debug_plan(int64_t N, int64_t M, int sms, int acc16, int64_t *out) { debug_plan(N, M, sms, acc16, out); }
 
 int gq_scores_f32(const float *mu, const float *std, const float *codebook, float *out, int64_t dim,
                   int64_t M, int64_t N, double beta, gq_stream_t stream)
@@ -108,6 +108,7 @@ int gq_codebook_create(const float *codebook, const float *nlp, int64_t N, int g
     cb->g = g;
     cb->kpad = gq_image_kpad(g);
     cb->n_pad = align_up(N, 128);
+    cb->n_pad2 = align_up(N, 256);
     cb->beta = beta;
     cudaGetDevice(&cb->device);
     int64_t off_cb = 0;
@@ -116,8 +117,8 @@ int gq_codebook_create(const float *codebook, const float *nlp, int64_t N, int g
     cb->kpad_robust = gq_has_robust_image(g) ? gq_image_kpad(g, true) : 0;
     cb->mode = GQ_MODE_AUTO;
     cb->usage_hist = nullptr;
-    int64_t off_bimg2 = align_up(off_bimg + cb->n_pad * cb->kpad * 2, 256);
-    int64_t off_meta = align_up(off_bimg2 + cb->n_pad * cb->kpad_robust * 2, 256);
+    int64_t off_bimg2 = align_up(off_bimg + cb->n_pad2 * cb->kpad * 2, 256);
+    int64_t off_meta = align_up(off_bimg2 + cb->n_pad2 * cb->kpad_robust * 2, 256);
     int64_t off_wide = align_up(off_meta + 4 * (3 + 2 * kMaxG), 256);
     int64_t total = off_wide + 256;
     cudaError_t e = cudaMalloc(&cb->base, (size_t)total);

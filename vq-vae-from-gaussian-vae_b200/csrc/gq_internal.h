@@ -45,7 +45,7 @@ int launch_quantize_latent(const gq_codebook *cb, const float *z, const float *e
 
 int debug_tc_scores(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
                     void *ws, int64_t ws_bytes, float *dump, float *wrow_out, cudaStream_t stream);
-void debug_plan(int64_t N, int64_t M, int sms, int64_t *out);
+void debug_plan(int64_t N, int64_t M, int sms, int acc16, int64_t *out);
 
 void prof_enable(int on);
 int prof_read(double *total_ms, int *count);

@@ -435,16 +435,16 @@ int launch_codebook_prep(gq_codebook *cb, const float *nlp_in, cudaStream_t stre
 {
     cudaError_t e = cudaMemsetAsync(cb->meta, 0, sizeof(float) * (3 + 2 * kMaxG), stream);
     if (e != cudaSuccess) { set_error("memset meta: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
-    int64_t blocks = (cb->n_pad + 255) / 256;
+    int64_t blocks = (cb->n_pad2 + 255) / 256;
     codebook_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(cb->cb, nlp_in, cb->nlpb, cb->bimg, cb->meta,
-                                                               cb->N, cb->n_pad, cb->g, cb->kpad, cb->beta,
+                                                               cb->N, cb->n_pad2, cb->g, cb->kpad, cb->beta,
                                                                gq_split_image(cb->g) ? 1 : 0, 1,
                                                                gq_acc16(cb->g, gq_split_image(cb->g)) ? 1 : 0);
     codebook_meta_finish_kernel<<<1, 1, 0, stream>>>(cb->meta, cb->g);
     count_launch(2);
     if (cb->kpad_robust) {   // second, split-precision image for the robust mode (nlpb / meta already written)
         codebook_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(cb->cb, nlp_in, cb->nlpb, cb->bimg_robust, cb->meta,
-                                                                   cb->N, cb->n_pad, cb->g, cb->kpad_robust, cb->beta, 1, 0, 0);
+                                                                   cb->N, cb->n_pad2, cb->g, cb->kpad_robust, cb->beta, 1, 0, 0);
         count_launch(1);
     }
     return check_launch("codebook_prep_kernel");

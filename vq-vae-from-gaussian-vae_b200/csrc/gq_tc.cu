@@ -111,6 +111,10 @@ constexpr int kCap = 32;             // chunk records per (row, segment)
 constexpr int kChunk = GQ_CHUNK;     // columns per recorded chunk (32 or 16); the rescoring kernels gather kChunk codewords per record
 static_assert(kChunk == 32 || kChunk == 16, "chunk width");
 constexpr int kMinStepsPerCta = 8;
+#ifndef GQ_PROD_BATCH
+#define GQ_PROD_BATCH 2
+#endif
+constexpr int kProdBatch = GQ_PROD_BATCH;   // codebook tiles the fp16-accumulator kernel's producer warp refills per loop trip
 #ifndef GQ_ALT_TILES
 #define GQ_ALT_TILES 1
 #endif
@@ -140,22 +144,30 @@ static_assert(sizeof(SegHdr) == 64, "segment summary must be 64 bytes");
 
 struct TcPlan {
     int64_t M, M_pad, N;
-    int units;           // ceil(M / 256)
-    int tiles;           // B tiles per unit = n_pad / 128
+    int unit_rows;       // rows per work unit: 256 (fp32 accumulators) or 128 (fp16 accumulators)
+    int tile_cols;       // codewords per tile: 128 or 256
+    int units;           // M_pad / unit_rows
+    int tiles;           // codebook tiles per unit = ceil(N / tile_cols)
     int64_t total_steps; // units * tiles
     int ctas;
     int steps_per_cta;
     int nseg;            // storage segments per row: kHalves x (max CTAs touching one unit)
 };
 
-static TcPlan make_plan_sms(int64_t N, int64_t n_pad, int64_t M, int sms)
+// Geometry of a search: the fp32-accumulator kernel works on units of 256 rows (two 128-row blocks per CTA)
+// and 128-codeword tiles; the fp16-accumulator kernel on units of 128 rows (one row block per CTA, its two
+// TMEM stages double-buffer 256-codeword tiles).  M_pad is a multiple of 256 either way, so the workspace
+// layout does not depend on which kernel a call uses (the search mode may change from call to call).
+static TcPlan make_plan_sms(int64_t N, int64_t M, int sms, bool acc16)
 {
     TcPlan p;
     p.M = M;
-    p.units = (int)((M + kUnitRows - 1) / kUnitRows);
-    p.M_pad = (int64_t)p.units * kUnitRows;
+    p.unit_rows = acc16 ? kBlockRows : kUnitRows;
+    p.tile_cols = acc16 ? 2 * kTileN : kTileN;
+    p.M_pad = (M + kUnitRows - 1) / kUnitRows * kUnitRows;
+    p.units = (int)(p.M_pad / p.unit_rows);
     p.N = N;
-    p.tiles = (int)(n_pad / kTileN);
+    p.tiles = (int)((N + p.tile_cols - 1) / p.tile_cols);
     p.total_steps = (int64_t)p.units * p.tiles;
     int64_t max_ctas = (p.total_steps + kMinStepsPerCta - 1) / kMinStepsPerCta;
     p.ctas = (int)imin(sms, imax(1, max_ctas));
@@ -165,10 +177,11 @@ static TcPlan make_plan_sms(int64_t N, int64_t n_pad, int64_t M, int sms)
     return p;
 }
 
-static TcPlan make_plan(const gq_codebook *cb, int64_t M)
-{
-    return make_plan_sms(cb->N, cb->n_pad, M, device_sm_count());
-}
+static bool use_robust_image(const gq_codebook *cb);
+
+// the plan of the NEXT call on this codebook (its search mode decides the kernel)
+static bool plan_acc16(const gq_codebook *cb) { return gq_acc16_wide(cb->g, gq_split_image(cb->g) || use_robust_image(cb)); }
+static TcPlan make_plan(const gq_codebook *cb, int64_t M) { return make_plan_sms(cb->N, M, device_sm_count(), plan_acc16(cb)); }
 
 struct TcWorkspace {
     __half *a_img;      // [M_pad, kpad] fp16, row-major
@@ -223,8 +236,11 @@ static TcWorkspace carve(const gq_codebook *cb, const TcPlan &p, void *base)
 int64_t tc_workspace_bytes(const gq_codebook *cb, int64_t M)
 {
     if (M <= 0) return 256;
-    TcPlan p = make_plan(cb, M);
-    return carve(cb, p, nullptr).bytes;
+    // the search mode (and with it the kernel geometry) may change between calls: size for the larger plan
+    const int sms = device_sm_count();
+    int64_t b = carve(cb, make_plan_sms(cb->N, M, sms, false), nullptr).bytes;
+    if (gq_acc16_wide(cb->g, gq_split_image(cb->g))) b = imax(b, carve(cb, make_plan_sms(cb->N, M, sms, true), nullptr).bytes);
+    return b;
 }
 
 // ---- 1. row preparation -----------------------------------------------------------------------
@@ -989,6 +1005,313 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     }
 }
 
+// ---- 2b. the search with fp16 accumulators: one row block per CTA, 256-codeword tiles ----------------------
+// scripts/ubench/mma_rate.cu: a kind::f16 tcgen05.mma with both operands in shared memory costs ~67 cycles plus
+// ~47 per 128 accumulator columns -- 114 cycles at N = 128 (56 % of the tensor rate: the 256 x 128 kernel above
+// sits exactly on that bound, 4 x 114 = 457 cycles per step), 161 at N = 256 (80 %).  This kernel therefore
+// contracts 256 codewords per instruction.  TMEM holds two 256-column stages, so a CTA owns ONE 128-row block
+// and double-buffers it properly; a work unit is 128 rows, a tile 16 KB of the codebook image (two adjacent
+// 128-codeword tiles: the image rows simply continue).  Warps: 8 epilogue (lane quarter q, stage s), 1 producer
+// (bulk async copies, kProdBatch slots per trip), 2 MMA issuers (one per stage: an issuer's per-tile chain is
+// ~400 cycles of serial latency against 322 tensor cycles per tile).  An epilogue warp owns one stage: per use it
+// pulls the whole 256-column tile as 128 packed registers, releases the stage at once and reduces four
+// 64-codeword groups with packed 3-input fp16 maxima (two 32-codeword chunks per group, gq_acc16_image_row).
+// Thread <-> (row, stage parity): two threads per row with independent running maxima / record lists, storage
+// segment 2 * piece + s, exactly the interface the re-scoring kernels expect.
+template <int KPAD>
+struct Tc16Smem {
+    static constexpr int kTileBytes = 2 * kTileN * KPAD * 2;            // 256 codewords
+    static constexpr int kABytes = kBlockRows * KPAD * 2;
+    static constexpr int kFit = (200 * 1024 - kABytes) / kTileBytes;
+    static constexpr int kStages = (kFit < 8 ? kFit : 8) & ~1;
+    static constexpr int kBOff = 0;
+    static constexpr int kAOff = kBOff + kStages * kTileBytes;
+    static constexpr int kBarOff = kAOff + kABytes;
+    // barriers: full_b[kStages], empty_b[kStages], a_full, acc_full[2], acc_empty[2]
+    static constexpr int kNumBars = 2 * kStages + 5;
+    static constexpr int kSlotOff = kBarOff + kNumBars * 8;
+    static constexpr int kBytes = kSlotOff + 16;
+};
+constexpr int kEpiWarps16 = 8;
+constexpr int kProducerWarp16 = kEpiWarps16, kIssuerWarp16 = kEpiWarps16 + 1;
+constexpr int kThreads16 = (kEpiWarps16 + 3) * 32;
+constexpr int kTile16 = 2 * kTileN;
+
+template <int KPAD, bool DUMP>
+__global__ void __launch_bounds__(kThreads16, 1)
+quantize_tc16_kernel(const __half *__restrict__ a_img, const __half *__restrict__ b_img,
+                     const float *__restrict__ wrow, SegHdr *__restrict__ seg_hdr, Cand *__restrict__ cand,
+                     uint32_t *__restrict__ rec_cnt, int64_t N, int tiles, int64_t total_steps, int steps_per_cta,
+                     int nseg, float *__restrict__ dump)
+{
+    using L = Tc16Smem<KPAD>;
+    constexpr int kStages = L::kStages;
+    static_assert(kHalves == 2 && kChunk == 32, "two watcher threads per row, 32-codeword chunks");
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t smem_base;
+    asm volatile("mov.u32 %0, %1;" : "=r"(smem_base) : "r"(smem_u32(smem)));
+    const uint32_t bar_base = smem_base + L::kBarOff;
+    auto full_b = [&](int i) { return bar_base + 8u * i; };
+    auto empty_b = [&](int i) { return bar_base + 8u * (kStages + i); };
+    const uint32_t a_full = bar_base + 8u * (2 * kStages);
+    auto acc_full = [&](int st) { return bar_base + 8u * (2 * kStages + 1 + st); };   // the MMA pair into stage st is complete
+    auto acc_empty = [&](int st) { return bar_base + 8u * (2 * kStages + 3 + st); };  // its four warps have drained stage st
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kSlotOff);
+
+    // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so that the service warps'
+    // counters, barrier and descriptor addresses live in uniform registers)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int cta = blockIdx.x;
+    const int64_t step_begin = (int64_t)cta * steps_per_cta;
+    const int64_t step_end = imin(step_begin + steps_per_cta, total_steps);
+    mbar_probe_declare();
+    pdl_launch_dependents();
+    GQ_TRACE_DECL();
+
+    if (warp == kIssuerWarp16 && lane == 0) {
+        uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kBarOff);
+        for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);               // full_b
+        for (int i = 0; i < kStages; ++i) mbar_init(&bars[kStages + i], 1);     // empty_b: the commit of the tile's MMAs
+        mbar_init(&bars[2 * kStages], 4);                                       // a_full: 4 warps
+        for (int i = 0; i < 2; ++i) mbar_init(&bars[2 * kStages + 1 + i], 1);   // acc_full
+        for (int i = 0; i < 2; ++i) mbar_init(&bars[2 * kStages + 3 + i], 4);   // acc_empty: the stage's 4 warps
+        fence_mbar_init();
+    }
+    if (warp == kIssuerWarp16) {
+        __syncwarp();
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == kProducerWarp16) {
+        // ===== producer: bulk async copies (TMA engine) of 256-codeword tiles, kProdBatch slots per trip =====
+        int64_t step = step_begin;
+        Piece p;
+        int stage = 0;
+        uint32_t phase = 0;
+        bool have = next_piece(step, step_end, tiles, steps_per_cta, cta, p);
+        int t = have ? p.t0 : 0;
+        while (have) {
+            int tt[kProdBatch], ss[kProdBatch];
+            uint32_t pp[kProdBatch];
+            int nb = 0;
+#pragma unroll
+            for (int i = 0; i < kProdBatch; ++i) {
+                if (have) {
+                    tt[i] = t; ss[i] = stage; pp[i] = phase ^ 1u;
+                    ++nb;
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    if (++t >= p.t1) { have = next_piece(step, step_end, tiles, steps_per_cta, cta, p); t = p.t0; }
+                } else { tt[i] = 0; ss[i] = 0; pp[i] = 0; }
+            }
+            GQ_TRACE(0);
+            if (nb == 2 && kProdBatch == 2) mbar_wait2_a(empty_b(ss[0]), pp[0], empty_b(ss[kProdBatch - 1]), pp[kProdBatch - 1]);
+            else {
+#pragma unroll
+                for (int i = 0; i < kProdBatch; ++i)
+                    if (i < nb) mbar_wait_a(empty_b(ss[i]), pp[i]);
+            }
+            GQ_TRACE(1);
+            if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < kProdBatch; ++i) {
+                    if (i < nb) {
+                        mbar_expect_tx_a(full_b(ss[i]), L::kTileBytes);
+                        bulk_g2s_a(smem_base + L::kBOff + ss[i] * L::kTileBytes,
+                                   reinterpret_cast<const char *>(b_img) + (int64_t)tt[i] * L::kTileBytes, L::kTileBytes, full_b(ss[i]));
+                    }
+                }
+            }
+            __syncwarp();
+            GQ_TRACE(2);
+            GQ_TRACE(3);
+            GQ_TRACE_NEXT();
+        }
+    } else if (warp == kIssuerWarp16 || warp == kIssuerWarp16 + 1) {
+        // ===== MMA issuers, one per accumulator stage: issuer s takes the tiles whose per-CTA count c is s mod 2.
+        // The whole warp runs the loop (warp-uniform control flow keeps the addresses on the uniform datapath), one
+        // elected lane issues to the tensor core. =====
+        const uint32_t st = (uint32_t)(warp - kIssuerWarp16);
+        constexpr uint32_t idesc = umma_idesc_f16(kBlockRows, kTile16, /*d_f32=*/false);
+        constexpr uint32_t kLbo = 128;              // K-adjacent core matrices
+        constexpr uint32_t kSbo = (KPAD / 8) * 128; // next 8-row group (rows 128..255 simply continue)
+        constexpr uint32_t desc_hi = ((kSbo >> 4) & 0x3FFFu) | (1u << 14);           // SBO, version = 1
+        const uint32_t desc_lo0 = (((smem_base + L::kBOff) >> 4) & 0x3FFFu) | (((kLbo >> 4) & 0x3FFFu) << 16);
+        const uint32_t adesc_lo0 = (((smem_base + L::kAOff) >> 4) & 0x3FFFu) | (((kLbo >> 4) & 0x3FFFu) << 16);
+        const uint32_t d = tmem_base + st * (uint32_t)kTile16;
+        int64_t step = step_begin;
+        Piece p;
+        uint32_t c = 0;       // tiles this CTA has processed before the current piece
+        int pi = 0;
+        while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
+            mbar_wait_a(a_full, pi & 1);
+            tc_fence_after();
+            const uint32_t c_end = c + (uint32_t)(p.t1 - p.t0);
+            for (uint32_t ci = c + ((c ^ st) & 1u); ci < c_end; ci += 2u) {
+                const uint32_t slot = ci % (uint32_t)kStages;
+                const uint32_t phase = (ci / (uint32_t)kStages) & 1u;
+                const uint32_t ep = ((ci >> 1) & 1u) ^ 1u;   // use u = ci / 2 of the stage waits for its (u-1)-th drain
+                GQ_TRACE_SET(ci);
+                GQ_TRACE(0);
+                mbar_wait2_a(full_b(slot), phase, acc_empty(st), ep);
+                GQ_TRACE(1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t desc_lo = desc_lo0 + slot * (uint32_t)(L::kTileBytes >> 4);
+#pragma unroll
+                    for (int j = 0; j < KPAD / 16; ++j) {
+                        // one K = 16 slice = two K-adjacent core matrices = 256 bytes in either operand
+                        const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(adesc_lo0 + j * 16);
+                        const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo + j * 16);
+                        umma_f16_ss(d, ad, bd, idesc, j > 0 ? 1u : 0u);
+                    }
+                    GQ_TRACE(2);
+                    umma_commit_a(acc_full(st));
+                    umma_commit_a(empty_b(slot));
+                }
+                __syncwarp();
+                GQ_TRACE(3);
+            }
+            c = c_end;
+            ++pi;
+        }
+    } else if (warp < kEpiWarps16) {
+        // ===== epilogue: (lane quarter q, stage s) =====
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int s = warp >> 2;
+        const uint32_t fbar = acc_full(s), ebar = acc_empty(s);
+        const uint32_t obar = acc_full(s ^ 1);   // the other stage
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kTile16);
+        const bool padded = (N % kTile16) != 0;
+        int pad_tile;
+        asm volatile("mov.b32 %0, %1;" : "=r"(pad_tile) : "r"(padded ? tiles - 1 : -1));
+        int64_t step = step_begin;
+        Piece p;
+        uint32_t c = 0;   // tiles this CTA has processed before the current piece
+        pdl_wait();       // the predecessor's rows / windows / segment headers are complete and visible from here on
+        while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
+            const int64_t row = (int64_t)p.unit * kBlockRows + q * 32 + lane;
+            const int sseg = p.seg * kHalves + s;
+            const uint32_t c_end = c + (uint32_t)(p.t1 - p.t0);
+            if (s == 0) {
+                // Row operand into shared memory.  Every MMA of the previous piece that read it must have completed.
+                // This warp consumed that piece's even tiles; if its last tile was an odd one, wait for that
+                // accumulator as well (a pure wait: the stage-1 warps drain it).
+                if (c > 0u && ((c - 1u) & 1u)) mbar_wait_a(obar, ((c - 1u) >> 1) & 1u);
+                store_a_row_smem<KPAD>(smem_base + L::kAOff, q * 32 + lane, a_img + row * KPAD);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(a_full);
+            }
+            const float w = wrow[row];
+            float runmax = -CUDART_INF_F;
+            float thr = (w >= 0.f) ? -CUDART_INF_F : CUDART_INF_F;
+#ifdef GQ_EXP_NOREC
+            thr = CUDART_INF_F;   // timing experiment only: the record path is never taken (results are wrong)
+#endif
+            uint32_t thr2 = pack_thr(thr);
+            uint32_t cnt = 0;
+            const uint32_t seg_index = (uint32_t)(row * nseg + sseg);   // < 2^32, checked on the host
+            Cand *list = cand + (int64_t)seg_index * kCap;
+            uint32_t ci = c + ((c ^ (uint32_t)s) & 1u);                 // first tile of the piece with our parity
+            int t = p.t0 + (int)(ci - c);
+            for (; ci < c_end; ci += 2u, t += 2) {
+                const uint32_t par = (ci >> 1) & 1u;                    // this is use number ci / 2 of the stage
+                GQ_TRACE_SET(ci);
+                GQ_TRACE(0);
+                mbar_probe_wait_a(fbar, par);
+                GQ_TRACE(1);
+                tc_fence_after();
+                // register 32 j + i (j = 64-codeword group 0..3): (codeword 64 j + i, codeword 64 j + 32 + i) of the tile
+                uint32_t pv[128];
+                tmem_ld_32x256p_sync(taddr, pv);
+                GQ_TRACE(2);
+                tc_fence_before();
+                if (lane == 0) mbar_arrive_a(ebar);
+                if constexpr (DUMP) {
+                    float *drow = dump + row * ((int64_t)tiles * kTile16) + (int64_t)t * kTile16;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { drow[64 * j + i] = half_lo(pv[32 * j + i]); drow[64 * j + 32 + i] = half_hi(pv[32 * j + i]); }
+                }
+                if (t == pad_tile) {
+                    // columns >= N hold the zero rows of the operand image: replace them with -inf
+                    const int n_in = (int)(N - (int64_t)t * kTile16);
+#pragma unroll
+                    for (int i = 0; i < 128; ++i) {
+                        const int lo_cw = (i >> 5) * 64 + (i & 31);
+                        if (lo_cw >= n_in) pv[i] = (pv[i] & 0xffff0000u) | 0xfc00u;
+                        if (lo_cw + 32 >= n_in) pv[i] = (pv[i] & 0x0000ffffu) | 0xfc000000u;
+                    }
+                }
+                uint32_t m2[4];                                  // (chunk 8t + 2j, chunk 8t + 2j + 1)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    m2[j] = chunk_max_packed(pv + 32 * j);
+                    if (j == 1) mbar_probe_a(fbar, par ^ 1u);    // the stage's next use: answered long before we ask again
+                }
+                if (hge2_any(hmax2(hmax2(m2[0], m2[1]), hmax2(m2[2], m2[3])), thr2)) {
+                    const uint32_t c0 = (uint32_t)t * (kTile16 / kChunk);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float ml = half_lo(m2[j]), mh = half_hi(m2[j]);
+                        if (ml >= thr) epi_record_t<true>(ml, c0 + 2u * j, w, runmax, thr, cnt, list);
+                        if (mh >= thr) epi_record_t<true>(mh, c0 + 2u * j + 1u, w, runmax, thr, cnt, list);
+                    }
+                    thr2 = pack_thr(thr);
+                }
+                GQ_TRACE(3);
+            }
+            c = c_end;
+            // piece done: filter this thread's own records against its final maximum and publish the survivors
+            {
+                SegHdr *hp = &seg_hdr[seg_index];
+                uint32_t ns = 0;
+                bool ovf = cnt > (uint32_t)kCap;
+                const float keep = win_thr(runmax, w, kWinRel16);
+                const uint32_t nrec = cnt < (uint32_t)kCap ? cnt : (uint32_t)kCap;
+                for (uint32_t i = 0; i < nrec; ++i) {
+                    const Cand cd = list[i];
+                    if (cd.score >= keep) {
+                        if (ns < (uint32_t)kSurv) hp->surv[ns] = cd;
+                        else ovf = true;
+                        ++ns;
+                    }
+                }
+                hp->runmax = runmax;
+                hp->cnt = ovf ? kSegOverflow : ns;
+                rec_cnt[seg_index] = cnt;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kIssuerWarp16) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// The search kernel of an operand image and its launch geometry.
+template <int G, int KPAD, bool SPLIT, bool DUMP>
+struct SearchKernel {
+    static constexpr bool kWide = gq_acc16_wide(G, SPLIT);
+    static constexpr int kSmem = kWide ? Tc16Smem<KPAD>::kBytes : TcSmem<KPAD>::kBytes;
+    static constexpr int kBlock = kWide ? kThreads16 : tc_threads(gq_acc16(G, SPLIT));
+    static auto fn()
+    {
+        if constexpr (kWide) return quantize_tc16_kernel<KPAD, DUMP>;
+        else return quantize_tc_kernel<KPAD, DUMP, gq_acc16(G, SPLIT)>;
+    }
+};
+
 // ---- 3. re-scoring of the recorded chunks: one warp per row, lane = codeword ----------------------
 constexpr int kRescoreWarps = 8;
 
@@ -1045,7 +1368,7 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
               const float *__restrict__ cb, const float *__restrict__ nlpb, const float *__restrict__ wrow,
               const SegHdr *__restrict__ seg_hdr, const Cand *__restrict__ cand, const uint32_t *__restrict__ rec_cnt,
               const uint32_t *__restrict__ rows, const uint32_t *__restrict__ row_chunks, const uint32_t *__restrict__ nrows, int64_t N, int tiles,
-              int steps_per_cta, int nseg, int64_t *__restrict__ idx_out, float *__restrict__ zhat_out,
+              int steps_per_cta, int nseg, int unit_rows, int64_t *__restrict__ idx_out, float *__restrict__ zhat_out,
               uint32_t *__restrict__ fb_rows, uint32_t *__restrict__ fb_count, unsigned long long *__restrict__ fb_keys,
               float win_rel)
 {
@@ -1090,7 +1413,7 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
             // parallel: lane s takes segment s for the running maxima, lane i takes record i of a list
             // (kCap = 32 = one record per lane, one coalesced load per segment); the survivors' chunk ids
             // are then broadcast one by one.  A single lane walking the lists cost 15 us per launch.
-            const uint32_t s0 = (uint32_t)(r / kUnitRows) * (uint32_t)tiles;
+            const uint32_t s0 = (uint32_t)(r / unit_rows) * (uint32_t)tiles;
             const int npieces = kHalves * ((int)((s0 + (uint32_t)tiles - 1u) / (uint32_t)steps_per_cta) - (int)(s0 / (uint32_t)steps_per_cta) + 1);
             float gmax = -CUDART_INF_F;
             for (int s = lane; s < npieces; s += 32) gmax = fmaxf(gmax, seg_hdr[r * nseg + s].runmax);
@@ -1514,11 +1837,10 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
                   int64_t *idx, float *zhat, const TcPlan &p, const TcWorkspace &w, uint32_t *stats,
                   float w_max, cudaStream_t stream, bool do_prep = true)
 {
-    using L = TcSmem<KPAD>;
+    using K = SearchKernel<G, KPAD, SPLIT, false>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(quantize_tc_kernel<KPAD, false, gq_acc16(G, SPLIT)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             L::kBytes);
+        cudaError_t e = cudaFuncSetAttribute(K::fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
         attr_set = true;
     }
@@ -1545,7 +1867,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
     }
     constexpr bool ACC16 = gq_acc16(G, SPLIT);
     constexpr float win_rel = ACC16 ? kWinRel16 : 0.f;
-    launch_chained(quantize_tc_kernel<KPAD, false, ACC16>, dim3(p.ctas), dim3(tc_threads(ACC16)), L::kBytes, stream,
+    launch_chained(K::fn(), dim3(p.ctas), dim3(K::kBlock), K::kSmem, stream,
                    w.a_img, (SPLIT && gq_has_robust_image(G)) ? cb->bimg_robust : cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N,
                    p.tiles, p.total_steps, p.steps_per_cta, p.nseg, nullptr);
     if (g_prof) {
@@ -1570,7 +1892,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
         if (rc) return rc;
         int sblocks = (int)imin((M + 3) / 4, (int64_t)device_sm_count() * 8);
         launch_chained(settle_kernel<G>, dim3(sblocks), dim3(128), 0, stream, mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.seg,
-                       w.cand, w.rec_cnt, w.st_rows, w.st_chunks, w.counters + 1, cb->N, p.tiles, p.steps_per_cta, p.nseg, idx, zhat,
+                       w.cand, w.rec_cnt, w.st_rows, w.st_chunks, w.counters + 1, cb->N, p.tiles, p.steps_per_cta, p.nseg, p.unit_rows, idx, zhat,
                        w.fb_rows, w.counters, w.fb_keys, win_rel);
     }
     rc = check_launch("settle_kernel");
@@ -1589,16 +1911,15 @@ static int run_tc_dump(const gq_codebook *cb, const float *mu, const float *std,
                        const TcPlan &p, const TcWorkspace &w, float *dump, float *wrow_out, float w_max,
                        cudaStream_t stream)
 {
-    using L = TcSmem<KPAD>;
-    cudaError_t e = cudaFuncSetAttribute(quantize_tc_kernel<KPAD, true, gq_acc16(G, SPLIT)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::kBytes);
+    using K = SearchKernel<G, KPAD, SPLIT, true>;
+    cudaError_t e = cudaFuncSetAttribute(K::fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
     rows_prep_kernel<G, KPAD, SPLIT><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
         mu, std, lstd, cb->meta, w.a_img, w.wrow, w.margin, w.seg, w.rec_cnt, p.nseg, M, p.M_pad, cb->beta, w_max,
         w.counters, w.counter_bytes / 4, cb->wide_dev);
     int rc = check_launch("rows_prep_kernel");
     if (rc) return rc;
-    quantize_tc_kernel<KPAD, true, gq_acc16(G, SPLIT)><<<p.ctas, tc_threads(gq_acc16(G, SPLIT)), L::kBytes, stream>>>(
+    K::fn()<<<p.ctas, K::kBlock, K::kSmem, stream>>>(
         w.a_img, (SPLIT && gq_has_robust_image(G)) ? cb->bimg_robust : cb->bimg, w.wrow, w.seg, w.cand, w.rec_cnt, cb->N, p.tiles, p.total_steps, p.steps_per_cta, p.nseg,
         dump);
     rc = check_launch("quantize_tc_kernel<dump>");
@@ -1806,7 +2127,7 @@ int launch_quantize_latent(const gq_codebook *cb, const float *z, const float *e
     if (C % cb->g) { set_error("channels %d not divisible by group %d", C, cb->g); return GQ_ERR_INVALID; }
     const int64_t M = b * l * (C / cb->g);
     if (M == 0) return GQ_OK;
-    if (M >= ((int64_t)1 << 31) || (M / kUnitRows + 1) * (cb->n_pad / kTileN) >= ((int64_t)1 << 31) ||
+    if (M >= ((int64_t)1 << 31) || (M / kBlockRows + 1) * (cb->n_pad / kTileN) >= ((int64_t)1 << 31) ||
         (M + kUnitRows) * make_plan(cb, M).nseg >= ((int64_t)1 << 32)) {
         set_error("problem too large: rows x codebook tiles must stay below 2^31");
         return GQ_ERR_INVALID;
@@ -1842,7 +2163,7 @@ int launch_quantize_tc(const gq_codebook *cb, const float *mu, const float *std,
                        cudaStream_t stream)
 {
     if (M == 0) return GQ_OK;
-    if (M >= ((int64_t)1 << 31) || (M / kUnitRows + 1) * (cb->n_pad / kTileN) >= ((int64_t)1 << 31) ||
+    if (M >= ((int64_t)1 << 31) || (M / kBlockRows + 1) * (cb->n_pad / kTileN) >= ((int64_t)1 << 31) ||
         (M + kUnitRows) * make_plan(cb, M).nseg >= ((int64_t)1 << 32)) {
         set_error("problem too large: rows x codebook tiles must stay below 2^31");
         return GQ_ERR_INVALID;
@@ -1893,10 +2214,11 @@ int debug_tc_scores(const gq_codebook *cb, const float *mu, const float *std, co
 
 // Host-only: the stream-K decomposition for (N, M) on `sms` SMs, for CPU-side tests.
 // out[0..5] = {units, tiles, ctas, steps_per_cta, nseg, M_pad}
-void debug_plan(int64_t N, int64_t M, int sms, int64_t *out)
+void debug_plan(int64_t N, int64_t M, int sms, int acc16, int64_t *out)
 {
-    TcPlan p = make_plan_sms(N, (N + kTileN - 1) / kTileN * kTileN, M, sms);
+    TcPlan p = make_plan_sms(N, M, sms, acc16 != 0);
     out[0] = p.units; out[1] = p.tiles; out[2] = p.ctas; out[3] = p.steps_per_cta; out[4] = p.nseg; out[5] = p.M_pad;
+    out[6] = p.unit_rows; out[7] = p.tile_cols;
 }
 
 }  // namespace gq

@@ -67,7 +67,7 @@ PROTOTYPES = {
     "gq_set_chained_launch": (None, [c_int]),
     "gq_debug_tc_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_void_p]),
-    "gq_debug_plan": (None, [c_int64, c_int64, c_int, POINTER(c_int64)]),
+    "gq_debug_plan": (None, [c_int64, c_int64, c_int, c_int, POINTER(c_int64)]),
 }
 
 _lib = None
