@@ -55,14 +55,14 @@ def main():
     for w in range(32):
         if t[w].any():
             roles[w] = w
-    issuers = [17, 18, 19, 20]
+    issuers = [17, 18]
     first = min(t[w, 0, 0] for w in roles)
     print("cycles relative to the first stamp.  I = issuer (top, B tile ready + stage drained, MMAs issued, committed + warp reconverged); "
           "E = epilogue warp (top, accumulator ready, data in registers, end of iteration)")
     ev = []
     for w in sorted(roles):
         name = f"I w{w}" if w in issuers else (f"P w{w}" if w == 16 else f"E w{w}")
-        if w not in (16, 17, 18, 19, 20, 0, 8, 4):
+        if w not in (16, 17, 18, 0, 8, 4):
             continue   # row block 0: its issuers (stage A / stage B) and two of its epilogue warps
         for i in range(10):
             ev.append((t[w, i, 0] - first, f"{name} it{300 + i}: " + " ".join(f"{int(x - first):6d}" for x in t[w, i])))

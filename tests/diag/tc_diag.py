@@ -48,7 +48,7 @@ def stage_dump(N, g, M):
     L = _lib.lib()
     L.gq_debug_plan.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     plan = (ctypes.c_int64 * 8)()
-    L.gq_debug_plan(N, M, 148, 1 if g in (8, 16) else 0, plan)
+    L.gq_debug_plan(N, M, 148, 0, plan)
     units, tiles, ctas, spc, nseg, M_pad, unit_rows, tile_cols = list(plan)
     n_pad = tiles * tile_cols
     ws = cb.workspace(M)
@@ -102,6 +102,9 @@ def stage_dump(N, g, M):
         s = s_used
         res["acc16"] = True
         res["bit_mismatch_frac_vs_emulation"] = float((G != d).mean())
+        mm = (G != d)
+        res["mismatch_by_rowblock128_x_tile128"] = [[round(float(mm[rb * 128:(rb + 1) * 128, t * 128:(t + 1) * 128].mean()), 3)
+                                                     for t in range(min(N // 128, 16))] for rb in range(min(M // 128, 4))]
     else:
         Ah = (A * s).astype(np.float32).astype(np.float16).astype(np.float64)
         G = Ah @ Bh.T
@@ -172,6 +175,8 @@ def stage_quantize(N, g, M, dist, exact_too=True, check_rows=4096):
 
 STAGES = {
     "dump_small": lambda: stage_dump(1024, 16, 256),
+    "dump_4k": lambda: stage_dump(4096, 16, 512),
+    "q_4k": lambda: stage_quantize(4096, 16, 512, "trained"),
     "dump_g4": lambda: stage_dump(4096, 4, 300),
     "dump_64k": lambda: stage_dump(65536, 16, 1024),
     "dump_g8": lambda: stage_dump(4096, 8, 300),
@@ -197,7 +202,7 @@ if __name__ == "__main__":
     for name in names:
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, __file__, "--stage", name], capture_output=True, text=True, timeout=75)
+            p = subprocess.run([sys.executable, __file__, "--stage", name], capture_output=True, text=True, timeout=40)
             tail = (p.stdout[-1500:] + p.stderr[-1500:]).strip()
             print(f"[{name}] rc={p.returncode} {time.time() - t0:.1f}s\n{tail}\n", flush=True)
         except subprocess.TimeoutExpired:

@@ -126,13 +126,15 @@ __host__ __device__ constexpr bool gq_has_robust_image(int g) { return g == 8 ||
 #define GQ_ACC16 1
 #endif
 __host__ __device__ constexpr bool gq_acc16(int g, bool split) { return GQ_ACC16 != 0 && !split && (g == 8 || g == 16); }
-// The fp16-accumulator search runs its own kernel geometry (gq_tc.cu quantize_tc16_kernel): one 128-row block per
-// CTA against 256-codeword tiles (tcgen05.mma M = 128, N = 256), because a K = 16 instruction costs ~67 cycles
-// whatever its N (scripts/ubench/mma_rate.cu).  -DGQ_ACC16_WIDE=0 keeps fp16 accumulators on the 256 x 128 geometry.
-#ifndef GQ_ACC16_WIDE
-#define GQ_ACC16_WIDE 1
+// Experimental (-DGQ_ACC16_TS=1): the fp16-accumulator search with its row operand in tensor memory (TS-form
+// tcgen05.mma, gq_tc.cu quantize_tc16_kernel).  The TS instruction is faster (87 vs 114 cycles, scripts/ubench/
+// mma_rate.cu) but leaves tensor memory for only three accumulator stages shared by the two row blocks; with the
+// column-half epilogue the kernel measured 0.268 ms against 0.205 ms for the SS form (profiles/README.md), correct on
+// the whole GPU suite.  Off by default.
+#ifndef GQ_ACC16_TS
+#define GQ_ACC16_TS 0
 #endif
-__host__ __device__ constexpr bool gq_acc16_wide(int g, bool split) { return GQ_ACC16_WIDE != 0 && gq_acc16(g, split); }
+__host__ __device__ constexpr bool gq_acc16_ts(int g, bool split) { return GQ_ACC16_TS != 0 && gq_acc16(g, split); }
 // image row (position in the MMA N dimension) of codeword n: half tile h = (n % 128) / 64, chunk parity
 // p = (n % 64) / 32, lane i = n % 32  ->  column 64 h + 2 i + p, i.e. packed register i = (chunk 2h, chunk 2h+1)
 __host__ __device__ constexpr int64_t gq_acc16_image_row(int64_t n)

@@ -180,7 +180,7 @@ static TcPlan make_plan_sms(int64_t N, int64_t M, int sms, bool acc16)
 static bool use_robust_image(const gq_codebook *cb);
 
 // the plan of the NEXT call on this codebook (its search mode decides the kernel)
-static bool plan_acc16(const gq_codebook *cb) { return gq_acc16_wide(cb->g, gq_split_image(cb->g) || use_robust_image(cb)); }
+static bool plan_acc16(const gq_codebook *) { return false; }   // every kernel in use works on 256-row units and 128-codeword tiles
 static TcPlan make_plan(const gq_codebook *cb, int64_t M) { return make_plan_sms(cb->N, M, device_sm_count(), plan_acc16(cb)); }
 
 struct TcWorkspace {
@@ -239,7 +239,6 @@ int64_t tc_workspace_bytes(const gq_codebook *cb, int64_t M)
     // the search mode (and with it the kernel geometry) may change between calls: size for the larger plan
     const int sms = device_sm_count();
     int64_t b = carve(cb, make_plan_sms(cb->N, M, sms, false), nullptr).bytes;
-    if (gq_acc16_wide(cb->g, gq_split_image(cb->g))) b = imax(b, carve(cb, make_plan_sms(cb->N, M, sms, true), nullptr).bytes);
     return b;
 }
 
@@ -1005,37 +1004,52 @@ quantize_tc_kernel(const __half *__restrict__ a_img, const __half *__restrict__ 
     }
 }
 
-// ---- 2b. the search with fp16 accumulators: one row block per CTA, 256-codeword tiles ----------------------
-// scripts/ubench/mma_rate.cu: a kind::f16 tcgen05.mma with both operands in shared memory costs ~67 cycles plus
-// ~47 per 128 accumulator columns -- 114 cycles at N = 128 (56 % of the tensor rate: the 256 x 128 kernel above
-// sits exactly on that bound, 4 x 114 = 457 cycles per step), 161 at N = 256 (80 %).  This kernel therefore
-// contracts 256 codewords per instruction.  TMEM holds two 256-column stages, so a CTA owns ONE 128-row block
-// and double-buffers it properly; a work unit is 128 rows, a tile 16 KB of the codebook image (two adjacent
-// 128-codeword tiles: the image rows simply continue).  Warps: 8 epilogue (lane quarter q, stage s), 1 producer
-// (bulk async copies, kProdBatch slots per trip), 2 MMA issuers (one per stage: an issuer's per-tile chain is
-// ~400 cycles of serial latency against 322 tensor cycles per tile).  An epilogue warp owns one stage: per use it
-// pulls the whole 256-column tile as 128 packed registers, releases the stage at once and reduces four
-// 64-codeword groups with packed 3-input fp16 maxima (two 32-codeword chunks per group, gq_acc16_image_row).
-// Thread <-> (row, stage parity): two threads per row with independent running maxima / record lists, storage
-// segment 2 * piece + s, exactly the interface the re-scoring kernels expect.
+// ---- 2b. the search with fp16 accumulators and the row operand in TENSOR MEMORY ------------------------------
+// What bounds the kernel above is neither arithmetic nor latency any more but the operand fetch of
+// tcgen05.mma: scripts/ubench/mma_rate.cu measures a kind::f16 instruction (K = 16) with both operands in
+// shared memory at 114 cycles for M = N = 128 -- 56 % of the tensor rate, and exactly the 4 x 114 = 457 cycles per
+// (256-row, 128-codeword) step the SS kernel runs at -- whatever the shared-memory layout; shared memory moves
+// ~90 B/cycle there (A 4 KB + B 4 KB per instruction, plus the tile copies).  With the row operand in tensor
+// memory (TS form) the same instruction takes 87 cycles and reads half the bytes.  The price is tensor memory:
+// 2 x 16 columns of row operand leave room for THREE 128-column accumulator stages, used round-robin by the
+// (tile, row block) sequence -- MMA-tile g = 2 c + rb of the CTA's running tile count c goes to stage g % 3 -- instead
+// of two private ones per row block.  fp16 accumulators keep the epilogue (packed loads, packed 3-input maxima)
+// short enough for that: a stage's round trip (MMA pair 175 cycles, wake-up, tcgen05.ld, release, issuer wake-up,
+// issue) is ~440 cycles, three stages deliver a tile every ~150.
+// Warps: 16 epilogue (row block, column half, lane quarter), producer, one MMA issuer per row block.
 template <int KPAD>
 struct Tc16Smem {
-    static constexpr int kTileBytes = 2 * kTileN * KPAD * 2;            // 256 codewords
-    static constexpr int kABytes = kBlockRows * KPAD * 2;
-    static constexpr int kFit = (200 * 1024 - kABytes) / kTileBytes;
-    static constexpr int kStages = (kFit < 8 ? kFit : 8) & ~1;
+    static constexpr int kBTileBytes = kTileN * KPAD * 2;
+    static constexpr int kFit = (200 * 1024) / kBTileBytes;
+    static constexpr int kStages = (kFit < 16 ? kFit : 16) & ~1;
     static constexpr int kBOff = 0;
-    static constexpr int kAOff = kBOff + kStages * kTileBytes;
-    static constexpr int kBarOff = kAOff + kABytes;
-    // barriers: full_b[kStages], empty_b[kStages], a_full, acc_full[2], acc_empty[2]
-    static constexpr int kNumBars = 2 * kStages + 5;
+    static constexpr int kBarOff = kBOff + kStages * kBTileBytes;
+    // barriers: full_b[kStages], empty_b[kStages], a_full[2], acc_full[3][2], acc_empty[3][2]
+    static constexpr int kNumBars = 2 * kStages + 2 + 12;
     static constexpr int kSlotOff = kBarOff + kNumBars * 8;
     static constexpr int kBytes = kSlotOff + 16;
 };
-constexpr int kEpiWarps16 = 8;
-constexpr int kProducerWarp16 = kEpiWarps16, kIssuerWarp16 = kEpiWarps16 + 1;
-constexpr int kThreads16 = (kEpiWarps16 + 3) * 32;
-constexpr int kTile16 = 2 * kTileN;
+constexpr int kAcc16Stages = 3;
+constexpr int kTmemACol = kAcc16Stages * kTileN;      // row operands: columns 384 + rb * KPAD / 2
+constexpr int kProducerWarp16 = kNumEpiWarps, kIssuerWarp16 = kNumEpiWarps + 1;
+constexpr int kThreads16 = (kNumEpiWarps + 3) * 32;
+
+// One row of the row-operand image (KPAD fp16) into the row's TMEM lane: two K-elements per 32-bit column.
+template <int KPAD>
+__device__ __forceinline__ void store_a_row_tmem(uint32_t taddr, const __half *__restrict__ a_row)
+{
+    constexpr int NW = KPAD / 2;
+    static_assert(NW == 8 || NW == 16, "K = 16 or 32");
+    uint32_t r[NW];
+#pragma unroll
+    for (int c = 0; c < NW / 4; ++c) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(a_row) + c);
+        r[4 * c + 0] = q.x; r[4 * c + 1] = q.y; r[4 * c + 2] = q.z; r[4 * c + 3] = q.w;
+    }
+    if constexpr (NW == 8) tmem_st_32x8(taddr, r);
+    else tmem_st_32x16(taddr, r);
+    tmem_st_wait();
+}
 
 template <int KPAD, bool DUMP>
 __global__ void __launch_bounds__(kThreads16, 1)
@@ -1046,16 +1060,22 @@ quantize_tc16_kernel(const __half *__restrict__ a_img, const __half *__restrict_
 {
     using L = Tc16Smem<KPAD>;
     constexpr int kStages = L::kStages;
-    static_assert(kHalves == 2 && kChunk == 32, "two watcher threads per row, 32-codeword chunks");
+    static_assert(kHalves == 2 && kChunk == 32, "column-half epilogue, 32-codeword chunks");
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t smem_base;
     asm volatile("mov.u32 %0, %1;" : "=r"(smem_base) : "r"(smem_u32(smem)));
     const uint32_t bar_base = smem_base + L::kBarOff;
     auto full_b = [&](int i) { return bar_base + 8u * i; };
     auto empty_b = [&](int i) { return bar_base + 8u * (kStages + i); };
-    const uint32_t a_full = bar_base + 8u * (2 * kStages);
-    auto acc_full = [&](int st) { return bar_base + 8u * (2 * kStages + 1 + st); };   // the MMA pair into stage st is complete
-    auto acc_empty = [&](int st) { return bar_base + 8u * (2 * kStages + 3 + st); };  // its four warps have drained stage st
+    auto a_full = [&](int i) { return bar_base + 8u * (2 * kStages + i); };                         // per row block
+    // A stage is used by the two row blocks ALTERNATELY (MMA-tiles g, g + 3, g + 6, ...), and the two issuers run
+    // independently, so a parity wait on a per-stage barrier would alias: a row block waiting for its use g + 6 cannot
+    // tell "g + 3 has not completed yet" from "g + 6 has".  Every (stage, row block) therefore has its own pair:
+    // acc_full(s, rb) is committed by rb's issuer and waited for by rb's warps (consecutive uses of s BY rb, g / 6 = 0, 1, ...);
+    // acc_empty(s, rb) collects the arrivals of rb's eight warps and is waited for by the OTHER row block's issuer,
+    // the stage's next user.  Each waiter sees consecutive phases of its barrier.
+    auto acc_full = [&](int st, int rb) { return bar_base + 8u * (2 * kStages + 2 + 2 * st + rb); };
+    constexpr uint32_t kEmptyOff = 8u * 2 * kAcc16Stages;                                           // acc_empty(s, rb) = acc_full(s, rb) + kEmptyOff
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kSlotOff);
 
     // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so that the service warps'
@@ -1071,11 +1091,11 @@ quantize_tc16_kernel(const __half *__restrict__ a_img, const __half *__restrict_
 
     if (warp == kIssuerWarp16 && lane == 0) {
         uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kBarOff);
-        for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);               // full_b
-        for (int i = 0; i < kStages; ++i) mbar_init(&bars[kStages + i], 1);     // empty_b: the commit of the tile's MMAs
-        mbar_init(&bars[2 * kStages], 4);                                       // a_full: 4 warps
-        for (int i = 0; i < 2; ++i) mbar_init(&bars[2 * kStages + 1 + i], 1);   // acc_full
-        for (int i = 0; i < 2; ++i) mbar_init(&bars[2 * kStages + 3 + i], 4);   // acc_empty: the stage's 4 warps
+        for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);                                  // full_b
+        for (int i = 0; i < kStages; ++i) mbar_init(&bars[kStages + i], 2);                        // empty_b: one commit per row block
+        for (int i = 0; i < 2; ++i) mbar_init(&bars[2 * kStages + i], 4);                          // a_full: 4 warps
+        for (int i = 0; i < 2 * kAcc16Stages; ++i) mbar_init(&bars[2 * kStages + 2 + i], 1);           // acc_full(s, rb)
+        for (int i = 0; i < 2 * kAcc16Stages; ++i) mbar_init(&bars[2 * kStages + 2 + 2 * kAcc16Stages + i], 4 * kHalves);   // acc_empty(s, rb): 8 warps
         fence_mbar_init();
     }
     if (warp == kIssuerWarp16) {
@@ -1089,124 +1109,101 @@ quantize_tc16_kernel(const __half *__restrict__ a_img, const __half *__restrict_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == kProducerWarp16) {
-        // ===== producer: bulk async copies (TMA engine) of 256-codeword tiles, kProdBatch slots per trip =====
+        // ===== producer: bulk async copies (TMA engine) of codebook tiles =====
         int64_t step = step_begin;
         Piece p;
         int stage = 0;
         uint32_t phase = 0;
-        bool have = next_piece(step, step_end, tiles, steps_per_cta, cta, p);
-        int t = have ? p.t0 : 0;
-        while (have) {
-            int tt[kProdBatch], ss[kProdBatch];
-            uint32_t pp[kProdBatch];
-            int nb = 0;
-#pragma unroll
-            for (int i = 0; i < kProdBatch; ++i) {
-                if (have) {
-                    tt[i] = t; ss[i] = stage; pp[i] = phase ^ 1u;
-                    ++nb;
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                    if (++t >= p.t1) { have = next_piece(step, step_end, tiles, steps_per_cta, cta, p); t = p.t0; }
-                } else { tt[i] = 0; ss[i] = 0; pp[i] = 0; }
-            }
-            GQ_TRACE(0);
-            if (nb == 2 && kProdBatch == 2) mbar_wait2_a(empty_b(ss[0]), pp[0], empty_b(ss[kProdBatch - 1]), pp[kProdBatch - 1]);
-            else {
-#pragma unroll
-                for (int i = 0; i < kProdBatch; ++i)
-                    if (i < nb) mbar_wait_a(empty_b(ss[i]), pp[i]);
-            }
-            GQ_TRACE(1);
-            if (elect_one()) {
-#pragma unroll
-                for (int i = 0; i < kProdBatch; ++i) {
-                    if (i < nb) {
-                        mbar_expect_tx_a(full_b(ss[i]), L::kTileBytes);
-                        bulk_g2s_a(smem_base + L::kBOff + ss[i] * L::kTileBytes,
-                                   reinterpret_cast<const char *>(b_img) + (int64_t)tt[i] * L::kTileBytes, L::kTileBytes, full_b(ss[i]));
-                    }
+        while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
+            for (int t = p.t0; t < p.t1; ++t) {
+                GQ_TRACE(0);
+                mbar_wait_a(empty_b(stage), phase ^ 1);
+                GQ_TRACE(1);
+                if (elect_one()) {
+                    mbar_expect_tx_a(full_b(stage), L::kBTileBytes);
+                    bulk_g2s_a(smem_base + L::kBOff + stage * L::kBTileBytes,
+                               reinterpret_cast<const char *>(b_img) + (int64_t)t * L::kBTileBytes, L::kBTileBytes, full_b(stage));
                 }
+                __syncwarp();
+                GQ_TRACE(2);
+                GQ_TRACE(3);
+                GQ_TRACE_NEXT();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            __syncwarp();
-            GQ_TRACE(2);
-            GQ_TRACE(3);
-            GQ_TRACE_NEXT();
         }
     } else if (warp == kIssuerWarp16 || warp == kIssuerWarp16 + 1) {
-        // ===== MMA issuers, one per accumulator stage: issuer s takes the tiles whose per-CTA count c is s mod 2.
-        // The whole warp runs the loop (warp-uniform control flow keeps the addresses on the uniform datapath), one
-        // elected lane issues to the tensor core. =====
-        const uint32_t st = (uint32_t)(warp - kIssuerWarp16);
-        constexpr uint32_t idesc = umma_idesc_f16(kBlockRows, kTile16, /*d_f32=*/false);
+        // ===== MMA issuers, one per row block.  The whole warp runs the loop (warp-uniform control flow keeps the
+        // addresses on the uniform datapath), one elected lane issues to the tensor core. =====
+        const int rb = warp - kIssuerWarp16;
+        constexpr uint32_t idesc = umma_idesc_f16(kBlockRows, kTileN, /*d_f32=*/false);
         constexpr uint32_t kLbo = 128;              // K-adjacent core matrices
-        constexpr uint32_t kSbo = (KPAD / 8) * 128; // next 8-row group (rows 128..255 simply continue)
+        constexpr uint32_t kSbo = (KPAD / 8) * 128; // next 8-row group
         constexpr uint32_t desc_hi = ((kSbo >> 4) & 0x3FFFu) | (1u << 14);           // SBO, version = 1
         const uint32_t desc_lo0 = (((smem_base + L::kBOff) >> 4) & 0x3FFFu) | (((kLbo >> 4) & 0x3FFFu) << 16);
-        const uint32_t adesc_lo0 = (((smem_base + L::kAOff) >> 4) & 0x3FFFu) | (((kLbo >> 4) & 0x3FFFu) << 16);
-        const uint32_t d = tmem_base + st * (uint32_t)kTile16;
+        const uint32_t a_t = tmem_base + (uint32_t)(kTmemACol + rb * (KPAD / 2));
         int64_t step = step_begin;
         Piece p;
-        uint32_t c = 0;       // tiles this CTA has processed before the current piece
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t g = (uint32_t)rb;   // MMA-tile number of this row block's next tile: g = 2 c + rb; stage g % 3
         int pi = 0;
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
-            mbar_wait_a(a_full, pi & 1);
+            mbar_wait_a(a_full(rb), pi & 1);
             tc_fence_after();
-            const uint32_t c_end = c + (uint32_t)(p.t1 - p.t0);
-            for (uint32_t ci = c + ((c ^ st) & 1u); ci < c_end; ci += 2u) {
-                const uint32_t slot = ci % (uint32_t)kStages;
-                const uint32_t phase = (ci / (uint32_t)kStages) & 1u;
-                const uint32_t ep = ((ci >> 1) & 1u) ^ 1u;   // use u = ci / 2 of the stage waits for its (u-1)-th drain
-                GQ_TRACE_SET(ci);
+            for (int t = p.t0; t < p.t1; ++t) {
+                const int as = (int)(g % 3u);
                 GQ_TRACE(0);
-                mbar_wait2_a(full_b(slot), phase, acc_empty(st), ep);
+                // the stage's previous user was the other row block, MMA-tile g - 3, its use number (g - 3) / 6 of the stage
+                // (none for g < 3: parity 1 passes on a fresh barrier)
+                mbar_wait2_a(full_b(stage), phase, acc_full(as, rb ^ 1) + kEmptyOff, ((g + 3u) / 6u + 1u) & 1u);
                 GQ_TRACE(1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t desc_lo = desc_lo0 + slot * (uint32_t)(L::kTileBytes >> 4);
+                    const uint32_t d = tmem_base + (uint32_t)(as * kTileN);
+                    const uint32_t desc_lo = desc_lo0 + (uint32_t)stage * (L::kBTileBytes >> 4);
 #pragma unroll
                     for (int j = 0; j < KPAD / 16; ++j) {
-                        // one K = 16 slice = two K-adjacent core matrices = 256 bytes in either operand
-                        const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(adesc_lo0 + j * 16);
+                        // one K = 16 slice: 8 columns of the row operand, two K-adjacent core matrices (256 bytes) of the tile
                         const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo + j * 16);
-                        umma_f16_ss(d, ad, bd, idesc, j > 0 ? 1u : 0u);
+                        umma_f16_ts(d, a_t + (uint32_t)(j * 8), bd, idesc, j > 0 ? 1u : 0u);
                     }
                     GQ_TRACE(2);
-                    umma_commit_a(acc_full(st));
-                    umma_commit_a(empty_b(slot));
+                    umma_commit_a(acc_full(as, rb));
+                    umma_commit_a(empty_b(stage));   // 2 arrivals (one per row block) free the slot
                 }
                 __syncwarp();
                 GQ_TRACE(3);
+                GQ_TRACE_NEXT();
+                g += 2u;
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            c = c_end;
             ++pi;
         }
-    } else if (warp < kEpiWarps16) {
-        // ===== epilogue: (lane quarter q, stage s) =====
+    } else if (warp < kNumEpiWarps) {
+        // ===== epilogue: (row block, column half, lane quarter).  Thread <-> (row, column half): two threads per row
+        // with independent running maxima / record lists, storage segment 2 * piece + half. =====
+        const int rb = (warp >> 2) & 1;
+        const int half = warp >> 3;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const int s = warp >> 2;
-        const uint32_t fbar = acc_full(s), ebar = acc_empty(s);
-        const uint32_t obar = acc_full(s ^ 1);   // the other stage
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kTile16);
-        const bool padded = (N % kTile16) != 0;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t tcol0 = tmem_base + lane_base + (uint32_t)(half * 64);
+        const bool padded = (N % kTileN) != 0;
         int pad_tile;
         asm volatile("mov.b32 %0, %1;" : "=r"(pad_tile) : "r"(padded ? tiles - 1 : -1));
         int64_t step = step_begin;
         Piece p;
-        uint32_t c = 0;   // tiles this CTA has processed before the current piece
-        pdl_wait();       // the predecessor's rows / windows / segment headers are complete and visible from here on
+        uint32_t g = (uint32_t)rb;   // MMA-tile number of this row block's next tile (as in the issuer)
+        pdl_wait();           // the predecessor's rows / windows / segment headers are complete and visible from here on
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
-            const int64_t row = (int64_t)p.unit * kBlockRows + q * 32 + lane;
-            const int sseg = p.seg * kHalves + s;
-            const uint32_t c_end = c + (uint32_t)(p.t1 - p.t0);
-            if (s == 0) {
-                // Row operand into shared memory.  Every MMA of the previous piece that read it must have completed.
-                // This warp consumed that piece's even tiles; if its last tile was an odd one, wait for that
-                // accumulator as well (a pure wait: the stage-1 warps drain it).
-                if (c > 0u && ((c - 1u) & 1u)) mbar_wait_a(obar, ((c - 1u) >> 1) & 1u);
-                store_a_row_smem<KPAD>(smem_base + L::kAOff, q * 32 + lane, a_img + row * KPAD);
-                fence_proxy_async_smem();
+            const int64_t row = (int64_t)p.unit * kUnitRows + rb * kBlockRows + q * 32 + lane;
+            const int sseg = p.seg * kHalves + half;
+            if (half == 0) {
+                // Row operand into tensor memory.  Every MMA of the previous piece that read this row block's operand
+                // has completed: this warp consumed that piece's last accumulator.
+                store_a_row_tmem<KPAD>(tmem_base + lane_base + (uint32_t)(kTmemACol + rb * (KPAD / 2)), a_img + row * KPAD);
+                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_a(a_full);
+                if (lane == 0) mbar_arrive_a(a_full(rb));
             }
             const float w = wrow[row];
             float runmax = -CUDART_INF_F;
@@ -1218,57 +1215,47 @@ quantize_tc16_kernel(const __half *__restrict__ a_img, const __half *__restrict_
             uint32_t cnt = 0;
             const uint32_t seg_index = (uint32_t)(row * nseg + sseg);   // < 2^32, checked on the host
             Cand *list = cand + (int64_t)seg_index * kCap;
-            uint32_t ci = c + ((c ^ (uint32_t)s) & 1u);                 // first tile of the piece with our parity
-            int t = p.t0 + (int)(ci - c);
-            for (; ci < c_end; ci += 2u, t += 2) {
-                const uint32_t par = (ci >> 1) & 1u;                    // this is use number ci / 2 of the stage
-                GQ_TRACE_SET(ci);
+            for (int t = p.t0; t < p.t1; ++t) {
+                const int as = (int)(g % 3u);
+                const uint32_t fbar = acc_full(as, rb);
                 GQ_TRACE(0);
-                mbar_probe_wait_a(fbar, par);
+                mbar_probe_wait_a(fbar, (g / 6u) & 1u);
                 GQ_TRACE(1);
                 tc_fence_after();
-                // register 32 j + i (j = 64-codeword group 0..3): (codeword 64 j + i, codeword 64 j + 32 + i) of the tile
-                uint32_t pv[128];
-                tmem_ld_32x256p_sync(taddr, pv);
+                // 64 fp16 scores as 32 packed registers: register i = (codeword 64*half + i, codeword 64*half + 32 + i)
+                // of the tile, i.e. (chunk 2*half, chunk 2*half + 1) -- the codebook image is stored in that order
+                uint32_t pv[32];
+                tmem_ld_32x64p_sync(tcol0 + (uint32_t)(as * kTileN), pv);
                 GQ_TRACE(2);
                 tc_fence_before();
-                if (lane == 0) mbar_arrive_a(ebar);
+                if (lane == 0) mbar_arrive_a(fbar + kEmptyOff);
+                g += 2u;
                 if constexpr (DUMP) {
-                    float *drow = dump + row * ((int64_t)tiles * kTile16) + (int64_t)t * kTile16;
+                    float *drow = dump + row * ((int64_t)tiles * kTileN) + (int64_t)t * kTileN + half * 64;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) { drow[64 * j + i] = half_lo(pv[32 * j + i]); drow[64 * j + 32 + i] = half_hi(pv[32 * j + i]); }
+                    for (int i = 0; i < 32; ++i) { drow[i] = half_lo(pv[i]); drow[32 + i] = half_hi(pv[i]); }
                 }
                 if (t == pad_tile) {
                     // columns >= N hold the zero rows of the operand image: replace them with -inf
-                    const int n_in = (int)(N - (int64_t)t * kTile16);
+                    const int n_in_half = (int)(N - (int64_t)t * kTileN) - half * 64;
 #pragma unroll
-                    for (int i = 0; i < 128; ++i) {
-                        const int lo_cw = (i >> 5) * 64 + (i & 31);
-                        if (lo_cw >= n_in) pv[i] = (pv[i] & 0xffff0000u) | 0xfc00u;
-                        if (lo_cw + 32 >= n_in) pv[i] = (pv[i] & 0x0000ffffu) | 0xfc000000u;
+                    for (int i = 0; i < 32; ++i) {
+                        if (i >= n_in_half) pv[i] = (pv[i] & 0xffff0000u) | 0xfc00u;
+                        if (32 + i >= n_in_half) pv[i] = (pv[i] & 0x0000ffffu) | 0xfc000000u;
                     }
                 }
-                uint32_t m2[4];                                  // (chunk 8t + 2j, chunk 8t + 2j + 1)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    m2[j] = chunk_max_packed(pv + 32 * j);
-                    if (j == 1) mbar_probe_a(fbar, par ^ 1u);    // the stage's next use: answered long before we ask again
-                }
-                if (hge2_any(hmax2(hmax2(m2[0], m2[1]), hmax2(m2[2], m2[3])), thr2)) {
-                    const uint32_t c0 = (uint32_t)t * (kTile16 / kChunk);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float ml = half_lo(m2[j]), mh = half_hi(m2[j]);
-                        if (ml >= thr) epi_record_t<true>(ml, c0 + 2u * j, w, runmax, thr, cnt, list);
-                        if (mh >= thr) epi_record_t<true>(mh, c0 + 2u * j + 1u, w, runmax, thr, cnt, list);
-                    }
+                mbar_probe_a(acc_full((int)(g % 3u), rb), (g / 6u) & 1u);      // this row block's next tile: the answer is there when we ask again
+                const uint32_t m2 = chunk_max_packed(pv);
+                if (hge2_any(m2, thr2)) {
+                    const float m0 = half_lo(m2), m1 = half_hi(m2);
+                    const uint32_t c0 = (uint32_t)t * (kTileN / kChunk) + (uint32_t)(half * 2);
+                    if (m0 >= thr) epi_record_t<true>(m0, c0, w, runmax, thr, cnt, list);
+                    if (m1 >= thr) epi_record_t<true>(m1, c0 + 1u, w, runmax, thr, cnt, list);
                     thr2 = pack_thr(thr);
                 }
                 GQ_TRACE(3);
+                GQ_TRACE_NEXT();
             }
-            c = c_end;
             // piece done: filter this thread's own records against its final maximum and publish the survivors
             {
                 SegHdr *hp = &seg_hdr[seg_index];
@@ -1302,7 +1289,7 @@ quantize_tc16_kernel(const __half *__restrict__ a_img, const __half *__restrict_
 // The search kernel of an operand image and its launch geometry.
 template <int G, int KPAD, bool SPLIT, bool DUMP>
 struct SearchKernel {
-    static constexpr bool kWide = gq_acc16_wide(G, SPLIT);
+    static constexpr bool kWide = gq_acc16_ts(G, SPLIT);   // fp16 accumulators + row operand in tensor memory
     static constexpr int kSmem = kWide ? Tc16Smem<KPAD>::kBytes : TcSmem<KPAD>::kBytes;
     static constexpr int kBlock = kWide ? kThreads16 : tc_threads(gq_acc16(G, SPLIT));
     static auto fn()
