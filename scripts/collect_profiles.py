@@ -3,8 +3,9 @@
 
     python scripts/collect_profiles.py r01
 
-Reads: gpurun_out/bench_r1.json, launches.csv (ncu launch list of the bench command),
+Reads (round r01): gpurun_out/bench_r1.json, launches.csv (ncu launch list of the bench command),
 prof_tc_final.ncu-rep (ncu --set full of quantize_tc_kernel), side_ncu_*.csv, side_kernels.json.
+Reads (later rounds): gpurun_out/<round>_bench_n1.json, <round>_launches.csv, <round>_prof_tc.ncu-rep, <round>_prof_side.ncu-rep.
 Writes: profiles/<round>_*.{json,csv,txt} and profiles/search_kernel_traffic.json (read by bench.py).
 """
 import csv
@@ -43,18 +44,18 @@ def main():
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
     summary = {"round": rnd}
-    b = os.path.join(OUT, "bench_r1.json")
+    b = os.path.join(OUT, "bench_r1.json" if rnd == "r01" else f"{rnd}_bench_n1.json")
     if os.path.exists(b):
         shutil.copy(b, os.path.join(PROF, f"{rnd}_bench_line.json"))
-        summary["bench"] = json.load(open(b))
-    l = os.path.join(OUT, "launches.csv")
+        summary["bench"] = json.loads(open(b).read().strip().splitlines()[-1])
+    l = os.path.join(OUT, "launches.csv" if rnd == "r01" else f"{rnd}_launches.csv")
     if os.path.exists(l):
         shutil.copy(l, os.path.join(PROF, f"{rnd}_ncu_launches.csv"))
         tab = launch_table(l)
         per_step = [(k, n, t) for k, n, t in tab if n >= 5]
         tot = sum(t for _, _, t in per_step)
         summary["launch_shares"] = [{"kernel": k, "launches": n, "avg_us": t / 1e3, "share_of_step": t / tot} for k, n, t in per_step]
-    rep = os.path.join(OUT, "prof_tc_final.ncu-rep")
+    rep = os.path.join(OUT, "prof_tc_final.ncu-rep" if rnd == "r01" else f"{rnd}_prof_tc.ncu-rep")
     if os.path.exists(rep):
         det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
         open(os.path.join(PROF, f"{rnd}_search_kernel_ncu_details.txt"), "w").write(det)
@@ -76,11 +77,15 @@ def main():
             return None
         rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
         if rd is not None and wr is not None:
-            json.dump({"kernel": "quantize_tc_kernel<32,0>", "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
+            json.dump({"kernel": "quantize_tc_kernel<32,0>" if rnd == "r01" else "quantize_tc_kernel<32,0,1> (fp16 accumulators)", "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
                        "source": f"ncu --set full, profiles/{rnd}_search_kernel_ncu_details.txt"},
                       open(os.path.join(PROF, "search_kernel_traffic.json"), "w"), indent=1)
+    srep = os.path.join(OUT, f"{rnd}_prof_side.ncu-rep")
+    if os.path.exists(srep):
+        det = subprocess.run(["ncu", "-i", srep, "--page", "details"], capture_output=True, text=True).stdout
+        open(os.path.join(PROF, f"{rnd}_side_kernels_ncu_details.txt"), "w").write(det)
     side = {}
-    for fn in sorted(glob.glob(os.path.join(OUT, "side_ncu_*.csv"))):
+    for fn in sorted(glob.glob(os.path.join(OUT, "side_ncu_*.csv"))) if rnd == "r01" else []:
         rows = list(csv.reader(open(fn)))
         hdr = None
         for i, r in enumerate(rows):
