@@ -64,6 +64,67 @@ __global__ void __launch_bounds__(128, 1) k(int mode, int acc16, int nacc, int i
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+
+// ---- cta_group::2: one instruction spans a CTA pair (M = 256: 128 rows per CTA; each CTA holds HALF of the N columns of B) ----
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(int n, int ts, int iters, unsigned long long *cycles)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = cluster_rank();
+    for (int i = threadIdx.x; i < (65536 + 65536) / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before(); __syncthreads(); cluster_sync_all(); tc_fence_after();
+    const uint32_t tmem = slot;
+    if (ts) {
+        uint32_t r[8];
+        for (int i = 0; i < 8; ++i) r[i] = 0x3c003c00u;
+        tmem_st_32x8(tmem + ((uint32_t)(warp * 32) << 16) + 480u, r);
+        tmem_st_wait();
+    }
+    tc_fence_before(); __syncthreads(); cluster_sync_all(); tc_fence_after();
+    if (rank == 0 && warp == 0 && elect_one()) {
+        const uint32_t idesc = (0u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        const uint32_t sa = smem_u32(smem), sb = sa + 65536;
+        const uint64_t ad = mk_desc(sa, 128, 256, 0);
+        const uint64_t bd = mk_desc(sb, 128, 256, 0);
+        const unsigned long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t d = tmem + (uint32_t)((i & 1) * (n <= 240 ? n : 0));
+            if (ts)
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                             ::"r"(d), "r"(tmem + 480u), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+            else
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+        mbar_wait(&bar, 0);
+        const unsigned long long t1 = clock64();
+        cycles[blockIdx.x / 2] = t1 - t0;
+    } else if (threadIdx.x == 0 && rank == 1) {
+        mbar_wait(&bar, 0);
+    }
+    __syncthreads();
+    tc_fence_before(); cluster_sync_all();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
 int main()
 {
     unsigned long long *cyc;
@@ -85,6 +146,18 @@ int main()
             const int n = (mode & 1) ? 256 : 128;
             const double per = avg / iters, ideal = 128.0 * n * 16 * 2 / 8192.0;
             printf("%-70s %s  %s  cycles/instruction %.1f (ideal %.0f)  tensor fraction %.2f\n", l.name, names[mode], cudaGetErrorString(e), per, ideal, ideal / per);
+        }
+    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 65536);
+    for (int ts = 0; ts < 2; ++ts)
+        for (int n : {128, 256}) {
+            k2<<<148, 128, 65536 + 65536>>>(n, ts, iters, cyc);
+            cudaError_t e = cudaDeviceSynchronize();
+            unsigned long long h[74];
+            cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+            double avg = 0; for (int i = 0; i < 74; ++i) avg += h[i]; avg /= 74;
+            const double per = avg / iters, ideal = 128.0 * n * 16 * 2 / 8192.0;   // per CTA: 128 rows x n columns
+            printf("cta_group::2 %s M256 (128 per CTA) N%d  %s  cycles/instruction %.1f (ideal %.0f per CTA)  tensor fraction %.2f\n", ts ? "TS" : "SS", n,
+                   cudaGetErrorString(e), per, ideal, ideal / per);
         }
     return 0;
 }

@@ -248,6 +248,13 @@ __device__ __forceinline__ void mbar_probe_a(uint32_t bar, uint32_t parity)
 {
     asm volatile("mbarrier.test_wait.parity.shared::cta.b64 gq_rdy, [%0], %1;" ::"r"(bar), "r"(parity) : "memory");
 }
+// The answer of the last mbar_probe_a as a value (use it only after independent work has been issued behind the probe).
+__device__ __forceinline__ bool mbar_probe_result()
+{
+    uint32_t ok;
+    asm volatile("selp.u32 %0, 1, 0, gq_rdy;" : "=r"(ok) :: "memory");
+    return ok != 0;
+}
 // Blocks until the phase is complete; free when the earlier probe already saw it.
 __device__ __forceinline__ void mbar_probe_wait_a(uint32_t bar, uint32_t parity)
 {

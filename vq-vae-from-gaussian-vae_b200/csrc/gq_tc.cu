@@ -111,6 +111,9 @@ constexpr int kCap = 32;             // chunk records per (row, segment)
 constexpr int kChunk = GQ_CHUNK;     // columns per recorded chunk (32 or 16); the rescoring kernels gather kChunk codewords per record
 static_assert(kChunk == 32 || kChunk == 16, "chunk width");
 constexpr int kMinStepsPerCta = 8;
+#ifndef GQ_FRONTEND_X4
+#define GQ_FRONTEND_X4 1     // group 16, plain image: four lanes per row in the fused front-end (0: one thread per row)
+#endif
 #ifndef GQ_PROD_BATCH
 #define GQ_PROD_BATCH 2
 #endif
@@ -1192,7 +1195,13 @@ quantize_tc16_kernel(const __half *__restrict__ a_img, const __half *__restrict_
         asm volatile("mov.b32 %0, %1;" : "=r"(pad_tile) : "r"(padded ? tiles - 1 : -1));
         int64_t step = step_begin;
         Piece p;
-        uint32_t g = (uint32_t)rb;   // MMA-tile number of this row block's next tile (as in the issuer)
+        // stage / barrier parity of the next tile to LOAD: MMA-tile g = 2 c + rb, stage g % 3, use g / 6 of acc_full(stage, rb)
+        int ld_as = rb, ld_g6 = rb;
+        uint32_t ld_par = 0;
+        auto ld_advance = [&]() {
+            ld_as += 2; if (ld_as >= kAcc16Stages) ld_as -= kAcc16Stages;
+            ld_g6 += 2; if (ld_g6 >= 6) { ld_g6 -= 6; ld_par ^= 1u; }
+        };
         pdl_wait();           // the predecessor's rows / windows / segment headers are complete and visible from here on
         while (next_piece(step, step_end, tiles, steps_per_cta, cta, p)) {
             const int64_t row = (int64_t)p.unit * kUnitRows + rb * kBlockRows + q * 32 + lane;
@@ -1215,21 +1224,20 @@ quantize_tc16_kernel(const __half *__restrict__ a_img, const __half *__restrict_
             uint32_t cnt = 0;
             const uint32_t seg_index = (uint32_t)(row * nseg + sseg);   // < 2^32, checked on the host
             Cand *list = cand + (int64_t)seg_index * kCap;
-            for (int t = p.t0; t < p.t1; ++t) {
-                const int as = (int)(g % 3u);
-                const uint32_t fbar = acc_full(as, rb);
-                GQ_TRACE(0);
-                mbar_probe_wait_a(fbar, (g / 6u) & 1u);
-                GQ_TRACE(1);
+
+            // Software pipeline over two register buffers: the NEXT tile's tcgen05.ld is issued before the current
+            // tile is reduced (if its accumulator is complete by then -- asked with an early test_wait probe whose
+            // answer is read only after the current buffer has been waited for and its stage released), so the load
+            // latency and the barrier round trip hide behind the ~250-cycle reduction instead of adding to it.
+            // 64 fp16 scores as 32 packed registers: register i = (codeword 64*half + i, codeword 64*half + 32 + i)
+            // of the tile, i.e. (chunk 2*half, chunk 2*half + 1) -- the codebook image is stored in that order.
+            auto issue_load = [&](uint32_t (&buf)[32], uint32_t &fbar_out) {
+                fbar_out = acc_full(ld_as, rb);
                 tc_fence_after();
-                // 64 fp16 scores as 32 packed registers: register i = (codeword 64*half + i, codeword 64*half + 32 + i)
-                // of the tile, i.e. (chunk 2*half, chunk 2*half + 1) -- the codebook image is stored in that order
-                uint32_t pv[32];
-                tmem_ld_32x64p_sync(tcol0 + (uint32_t)(as * kTileN), pv);
-                GQ_TRACE(2);
-                tc_fence_before();
-                if (lane == 0) mbar_arrive_a(fbar + kEmptyOff);
-                g += 2u;
+                tmem_ld_32x64p(tcol0 + (uint32_t)(ld_as * kTileN), buf);
+                ld_advance();
+            };
+            auto process = [&](uint32_t (&pv)[32], int t) {
                 if constexpr (DUMP) {
                     float *drow = dump + row * ((int64_t)tiles * kTileN) + (int64_t)t * kTileN + half * 64;
 #pragma unroll
@@ -1244,7 +1252,6 @@ quantize_tc16_kernel(const __half *__restrict__ a_img, const __half *__restrict_
                         if (32 + i >= n_in_half) pv[i] = (pv[i] & 0x0000ffffu) | 0xfc000000u;
                     }
                 }
-                mbar_probe_a(acc_full((int)(g % 3u), rb), (g / 6u) & 1u);      // this row block's next tile: the answer is there when we ask again
                 const uint32_t m2 = chunk_max_packed(pv);
                 if (hge2_any(m2, thr2)) {
                     const float m0 = half_lo(m2), m1 = half_hi(m2);
@@ -1253,8 +1260,31 @@ quantize_tc16_kernel(const __half *__restrict__ a_img, const __half *__restrict_
                     if (m1 >= thr) epi_record_t<true>(m1, c0 + 1u, w, runmax, thr, cnt, list);
                     thr2 = pack_thr(thr);
                 }
+            };
+            // one pipeline step: `cur` holds tile t (its load is in flight), `nxt` receives tile t + 1 if there is one
+            auto pipe_step = [&](uint32_t (&cur)[32], uint32_t fbar_cur, uint32_t (&nxt)[32], uint32_t &fbar_nxt, int t) {
+                const bool more = t + 1 < p.t1;
+                GQ_TRACE(0);
+                if (more) mbar_probe_a(acc_full(ld_as, rb), ld_par);     // asynchronous: answered while we wait for `cur`
+                tmem_ld_wait_p(cur);
+                GQ_TRACE(1);
+                tc_fence_before();
+                if (lane == 0) mbar_arrive_a(fbar_cur + kEmptyOff);
+                bool issued = false;
+                if (more && mbar_probe_result()) { issue_load(nxt, fbar_nxt); issued = true; }
+                GQ_TRACE(2);
+                process(cur, t);
+                if (more && !issued) { mbar_wait_a(acc_full(ld_as, rb), ld_par); issue_load(nxt, fbar_nxt); }
                 GQ_TRACE(3);
                 GQ_TRACE_NEXT();
+            };
+            uint32_t bufA[32], bufB[32];
+            uint32_t fbarA = 0, fbarB = 0;
+            mbar_wait_a(acc_full(ld_as, rb), ld_par);
+            issue_load(bufA, fbarA);
+            for (int t = p.t0; t < p.t1; t += 2) {
+                pipe_step(bufA, fbarA, bufB, fbarB, t);
+                if (t + 1 < p.t1) pipe_step(bufB, fbarB, bufA, fbarA, t + 1);
             }
             // piece done: filter this thread's own records against its final maximum and publish the survivors
             {
@@ -1988,6 +2018,140 @@ frontend_kernel(const float *__restrict__ z, const float *__restrict__ eps, cons
                       seg_hdr + r * nseg, rec_cnt + r * nseg, nseg, wide_dev);
 }
 
+// The same front-end for the plain fp16 image of group 16 with FOUR lanes per row (each lane takes four of the
+// sixteen dimensions): the thread-per-row kernel above walks ~2 K dependent instructions per row on 64 K threads
+// (33 % of the HBM rate at batch 64, and 13 us for ONE image, where it occupies eight SMs); here the per-row
+// sums and maxima of the window are folded over the four lanes with two shuffles each.  The window is a set of
+// upper bounds, so the different summation order only moves it within its 1 % slack; everything that defines
+// results -- mu, std = exp(0.5 clamp(logvar)), log(std), zhat_noquant and the fp16 image values -- is computed per
+// element exactly as above.
+template <int KPAD>
+__global__ void __launch_bounds__(256)
+frontend16x4_kernel(const float *__restrict__ z, const float *__restrict__ eps, const float *__restrict__ meta,
+                    float *__restrict__ mu_r, float *__restrict__ std_r, float *__restrict__ zhat_nq,
+                    __half *__restrict__ a_img, float *__restrict__ wrow, float *__restrict__ margin_out,
+                    uint32_t *__restrict__ rec_cnt, int nseg, int64_t b, int64_t l, int C, int layout, float lv_lo,
+                    float lv_hi, int64_t M, int64_t M_pad, float beta, float w_max, uint32_t *__restrict__ counters,
+                    int64_t counter_words, uint32_t *__restrict__ wide_dev)
+{
+    constexpr int G = 16, DL = 4;
+    static_assert(KPAD == 32, "plain image of group 16");
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < counter_words) counters[gid] = 0u;   // device-side lists / arrival counters of this call (counter_words <= M_pad)
+    const int64_t i = gid >> 2;
+    const int sub = (int)(gid & 3);
+    if (i >= M_pad) return;                        // whole quads leave together
+    const int ncb = C / G;
+    const bool valid = i < M;
+    int64_t r = i;
+    float a[DL], bq[DL];
+    float amax = 0.f, bnorm2 = 0.f, R = 0.f, p_naive = 0.f, maxA = 0.f, sumA = 0.f, eA = 0.f;
+    if (valid) {
+        int64_t zb, zs, lvo, eb, es;
+        if (layout == GQ_LAYOUT_BCHW) {
+            const int64_t t = i % l;
+            const int j = (int)((i / l) % ncb);
+            const int64_t bi = i / (l * ncb);
+            zb = (bi * 2 * C + j) * l + t;
+            zs = (int64_t)ncb * l;
+            lvo = (int64_t)C * l;
+            r = (bi * l + t) * ncb + j;
+            eb = (bi * C + j) * l + t;
+            es = (int64_t)ncb * l;
+        } else {
+            const int j = (int)(i % ncb);
+            const int64_t tok = i / ncb;
+            zb = tok * 2 * C + j;
+            zs = ncb;
+            lvo = C;
+            eb = tok * C + j;
+            es = ncb;
+        }
+        float m[DL], sd[DL];
+#pragma unroll
+        for (int kk = 0; kk < DL; ++kk) {
+            const int k = sub * DL + kk;
+            m[kk] = __ldg(z + zb + k * zs);
+            const float lv = clamp_torch(__ldg(z + zb + lvo + k * zs), lv_lo, lv_hi);
+            sd[kk] = expf(__fmul_rn(0.5f, lv));
+            const float ls = logf(sd[kk]);
+            if (zhat_nq) zhat_nq[eb + k * es] = __fadd_rn(m[kk], __fmul_rn(__ldg(eps + eb + k * es), sd[kk]));
+            const float v = sd[kk] * sd[kk];
+            const float rr = 0.5f / v;                  // 1/(2v)
+            a[kk] = 0.5f * beta - rr;
+            bq[kk] = m[kk] / v;
+            const float x2m = meta[2 + k], xm = meta[2 + G + k];
+            amax = fmaxf(amax, fabsf(a[kk]));
+            bnorm2 = fmaf(bq[kk], bq[kk], bnorm2);
+            maxA = fmaxf(maxA, fmaxf(fabsf(a[kk]), fabsf(bq[kk])));
+            p_naive += fabsf(a[kk]) * x2m + fabsf(bq[kk]) * xm;
+            sumA += fabsf(a[kk]) + fabsf(bq[kk]);
+            eA += (0.5f * beta + rr) * x2m + fabsf(bq[kk]) * xm;
+            const float q = xm + fabsf(m[kk]);
+            R += q * q * rr + fabsf(ls) + 2.0f * fmaxf(1.0f, beta) + beta * x2m;
+        }
+        reinterpret_cast<float4 *>(mu_r + r * G)[sub] = make_float4(m[0], m[1], m[2], m[3]);
+        reinterpret_cast<float4 *>(std_r + r * G)[sub] = make_float4(sd[0], sd[1], sd[2], sd[3]);
+        for (int sgi = sub; sgi < nseg; sgi += 4) rec_cnt[r * nseg + sgi] = 0u;   // (see prep_row: only the counters are cleared)
+    } else {
+#pragma unroll
+        for (int kk = 0; kk < DL; ++kk) { a[kk] = 0.f; bq[kk] = 0.f; }
+    }
+    // fold the four lanes of the row (xor 1, 2 stay inside the quad; the whole warp is here: quads leave together)
+#pragma unroll
+    for (int off = 1; off <= 2; off <<= 1) {
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+        maxA = fmaxf(maxA, __shfl_xor_sync(0xffffffffu, maxA, off));
+        bnorm2 += __shfl_xor_sync(0xffffffffu, bnorm2, off);
+        R += __shfl_xor_sync(0xffffffffu, R, off);
+        p_naive += __shfl_xor_sync(0xffffffffu, p_naive, off);
+        sumA += __shfl_xor_sync(0xffffffffu, sumA, off);
+        eA += __shfl_xor_sync(0xffffffffu, eA, off);
+    }
+    bool bad = !valid;
+    if (!(maxA > 0.f) || !isfinite(maxA) || !isfinite(R) || !isfinite(bnorm2)) bad = true;
+    float scale = 1.f, w_scaled = -1.f, margin = 0.f;
+    bool wide = false;
+    if (!bad) {       // the window of prep_row<16, 32, false> (fp16 accumulators), term by term
+        int ex, exp_p;
+        frexpf(maxA, &ex);
+        const float u2 = sqrtf(bnorm2) * 1.000001f * meta[1];
+        const float p_norm = amax * meta[0] + u2;
+        const float P = fminf(p_naive, p_norm);
+        frexpf(P * 1.002f, &exp_p);
+        scale = gq_acc16(G, false) ? ldexpf(1.0f, imin(15 - exp_p, 15 - ex)) : ldexpf(1.0f, 8 - ex);
+        if (!isfinite(P) || !(scale > 0.f) || !isfinite(scale)) bad = true;
+        const float sumB = meta[2 + 2 * kMaxG];
+        const float e_round = 1.01f * ldexpf(P, -10);
+        const float e_floor = ldexpf(sumB / scale + sumA, -25);
+        const float e_acc = gq_acc16(G, false) ? 1.004f * ldexpf(fminf(u2, amax * meta[0]), -11) + ldexpf(1.0f / scale, -24) : 0.f;
+        const float e_tc = e_round + e_floor + ldexpf(eA, -22) + e_acc;
+        const float W = 2.02f * (e_tc + ldexpf(R, -20));
+        margin = 2.02f * 4.0f * ldexpf(R, -20);
+        if (!(W <= w_max) || !isfinite(W * scale)) bad = true;
+        else w_scaled = W * scale * 1.001f;
+        wide = !(W <= w_max);      // plain image: W is the plain window (GQ_MODE_AUTO feedback)
+    }
+    {
+        const unsigned mw = __ballot_sync(0xffffffffu, wide && sub == 0 && valid);
+        if (mw && (threadIdx.x & 31) == (unsigned)(__ffs(mw) - 1)) atomicAdd(wide_dev, (uint32_t)__popc(mw));
+    }
+    // fp16 image row [a(16) | b(16)]: this lane's four a's and four b's, 8 bytes each
+    __half2 ha[2], hb[2];
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+        ha[h2] = __floats2half2_rn(bad ? 0.f : a[2 * h2] * scale, bad ? 0.f : a[2 * h2 + 1] * scale);
+        hb[h2] = __floats2half2_rn(bad ? 0.f : bq[2 * h2] * scale, bad ? 0.f : bq[2 * h2 + 1] * scale);
+    }
+    __half *arow = a_img + r * KPAD;
+    *reinterpret_cast<uint2 *>(arow + sub * DL) = *reinterpret_cast<uint2 *>(ha);
+    *reinterpret_cast<uint2 *>(arow + G + sub * DL) = *reinterpret_cast<uint2 *>(hb);
+    if (sub == 0) {
+        wrow[r] = w_scaled;
+        margin_out[r] = margin;
+    }
+}
+
 // Row indices -> the module's output tensors (gaussian.py:153-158): indices [b,l,ncb] / [b,ncb,h,w]
 // and zhat [b,l,C] / [b,C,h,w] with channel k*ncb + j = codebook[idx][k].
 template <int G>
@@ -2081,9 +2245,15 @@ static int run_latent(const gq_codebook *cb, const float *z, const float *eps, i
     const int64_t M = b * l * ncb;
     TcPlan p = make_plan(cb, M);
     TcWorkspace w = carve(cb, p, lw.tc);
-    frontend_kernel<G, KPAD, SPLIT><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
-        z, eps, cb->meta, lw.mu_r, lw.std_r, zhat_nq, w.a_img, w.wrow, w.margin, w.seg, w.rec_cnt, p.nseg, b, l, C,
-        layout, lv_lo, lv_hi, M, p.M_pad, cb->beta, g_w_max, w.counters, w.counter_bytes / 4, cb->wide_dev);
+    if constexpr (G == 16 && !SPLIT && GQ_FRONTEND_X4) {
+        frontend16x4_kernel<KPAD><<<(unsigned)((p.M_pad * 4 + 255) / 256), 256, 0, stream>>>(
+            z, eps, cb->meta, lw.mu_r, lw.std_r, zhat_nq, w.a_img, w.wrow, w.margin, w.rec_cnt, p.nseg, b, l, C,
+            layout, lv_lo, lv_hi, M, p.M_pad, cb->beta, g_w_max, w.counters, w.counter_bytes / 4, cb->wide_dev);
+    } else {
+        frontend_kernel<G, KPAD, SPLIT><<<(unsigned)((p.M_pad + 127) / 128), 128, 0, stream>>>(
+            z, eps, cb->meta, lw.mu_r, lw.std_r, zhat_nq, w.a_img, w.wrow, w.margin, w.seg, w.rec_cnt, p.nseg, b, l, C,
+            layout, lv_lo, lv_hi, M, p.M_pad, cb->beta, g_w_max, w.counters, w.counter_bytes / 4, cb->wide_dev);
+    }
     int rc = check_launch("frontend_kernel");
     if (rc) return rc;
     count_launch(1);
