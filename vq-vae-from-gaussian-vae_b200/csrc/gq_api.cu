@@ -120,7 +120,9 @@ int gq_codebook_create(const float *codebook, const float *nlp, int64_t N, int g
     int64_t off_bimg2 = align_up(off_bimg + cb->n_pad2 * cb->kpad * 2, 256);
     int64_t off_meta = align_up(off_bimg2 + cb->n_pad2 * cb->kpad_robust * 2, 256);
     int64_t off_wide = align_up(off_meta + 4 * (3 + 2 * kMaxG), 256);
-    int64_t total = off_wide + 256;
+    int64_t off_sortv = off_wide + 256;
+    int64_t off_sorti = align_up(off_sortv + N * g * 4, 256);
+    int64_t total = align_up(off_sorti + N * g * 4, 256);
     cudaError_t e = cudaMalloc(&cb->base, (size_t)total);
     if (e != cudaSuccess) { set_error("gq_codebook_create: cudaMalloc(%lld): %s", (long long)total, cudaGetErrorString(e)); delete cb; return GQ_ERR_CUDA; }
     char *b = reinterpret_cast<char *>(cb->base);
@@ -130,6 +132,8 @@ int gq_codebook_create(const float *codebook, const float *nlp, int64_t N, int g
     cb->meta = reinterpret_cast<float *>(b + off_meta);
     cb->bimg_robust = cb->kpad_robust ? reinterpret_cast<__half *>(b + off_bimg2) : nullptr;
     cb->wide_dev = reinterpret_cast<uint32_t *>(b + off_wide);
+    cb->sort_val = reinterpret_cast<float *>(b + off_sortv);
+    cb->sort_idx = reinterpret_cast<uint32_t *>(b + off_sorti);
     // feedback word for GQ_MODE_AUTO: pinned + mapped, written by the last kernel of a call, read by the
     // host when it sets up the next one (never synchronised on)
     cb->fb_host = nullptr;

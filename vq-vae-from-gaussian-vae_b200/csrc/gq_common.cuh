@@ -198,4 +198,8 @@ struct gq_codebook {
     volatile uint32_t *fb_host;   // pinned, mapped: [0] = such rows in the last completed call, [1] = its row count
     uint32_t *fb_dev;         // device view of fb_host
     unsigned long long *usage_hist;   // optional device uint64[N]: gq_quantize_latent accumulates its indices into it
+    // per-dimension sorted view of the codebook (pruned exact scan of the rows the search cannot certify, gq_tc.cu):
+    // sort_val[k*N + p] = p-th smallest x_k, sort_idx[k*N + p] = the codeword it belongs to
+    float *sort_val;
+    uint32_t *sort_idx;
 };

@@ -7,6 +7,8 @@
 #include "gq_common.cuh"
 #include "gq_internal.h"
 
+#include <cub/device/device_radix_sort.cuh>
+
 namespace gq {
 
 // ------------------------------------------------------------------------------------------
@@ -431,6 +433,39 @@ __global__ void codebook_meta_finish_kernel(float *meta, int g)
     meta[2 + 2 * kMaxG] = s * 1.000001f;
 }
 
+__global__ void column_keys_kernel(const float *__restrict__ cb, int64_t N, int g, int k, float *__restrict__ keys,
+                                   uint32_t *__restrict__ vals)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) { keys[n] = cb[n * g + k]; vals[n] = (uint32_t)n; }
+}
+
+// sort_val / sort_idx: every codebook column sorted ascending with its codeword ids (cub radix sort, once per
+// codebook, off the hot path; the scratch buffers are freed again)
+static int build_sorted_columns(gq_codebook *cb, cudaStream_t stream)
+{
+    const int64_t N = cb->N;
+    float *keys = nullptr;
+    uint32_t *vals = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, cb->sort_val, vals, cb->sort_idx, (int)N, 0, 32, stream);
+    if (e == cudaSuccess) e = cudaMalloc(&keys, (size_t)N * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&vals, (size_t)N * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
+    for (int k = 0; k < cb->g && e == cudaSuccess; ++k) {
+        column_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(cb->cb, N, cb->g, k, keys, vals);
+        e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, cb->sort_val + (int64_t)k * N, vals, cb->sort_idx + (int64_t)k * N,
+                                            (int)N, 0, 32, stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(keys);
+    cudaFree(vals);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { set_error("codebook column sort: %s", cudaGetErrorString(e)); return GQ_ERR_CUDA; }
+    return GQ_OK;
+}
+
 int launch_codebook_prep(gq_codebook *cb, const float *nlp_in, cudaStream_t stream)
 {
     cudaError_t e = cudaMemsetAsync(cb->meta, 0, sizeof(float) * (3 + 2 * kMaxG), stream);
@@ -447,7 +482,9 @@ int launch_codebook_prep(gq_codebook *cb, const float *nlp_in, cudaStream_t stre
                                                                    cb->N, cb->n_pad2, cb->g, cb->kpad_robust, cb->beta, 1, 0, 0);
         count_launch(1);
     }
-    return check_launch("codebook_prep_kernel");
+    int rc = check_launch("codebook_prep_kernel");
+    if (rc) return rc;
+    return build_sorted_columns(cb, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -192,7 +192,8 @@ struct TcWorkspace {
     float *margin;      // [M_pad] prefilter margin (unscaled score units)
     SegHdr *seg;        // [M_pad, nseg]
     Cand *cand;         // [M_pad, nseg, kCap]
-    uint32_t *fb_rows;  // [M] fallback row list (exact scan)
+    uint32_t *fb_rows;  // [M] rows the rescoring kernels could not certify (pruned exact scan inside settle_kernel); count = counters[0]
+    uint32_t *fb_rows2; // [M] rows left for the sliced full scan (from the pruned scan and from settle_kernel); count = counters[2]
     uint32_t *st_rows;  // [M] rows whose prefilter left several contenders (settle_kernel); bit 31: use the full record list
     uint32_t *st_chunks; // [M][8] per listed row: {number of surviving chunks (<= 7, else ~0), chunk ids}: saves settle the re-derivation
     uint32_t *rec_cnt;  // [M_pad, nseg] records written per (row, segment) (may exceed kCap: list overflow)
@@ -220,6 +221,8 @@ static TcWorkspace carve(const gq_codebook *cb, const TcPlan &p, void *base)
     w.cand = reinterpret_cast<Cand *>(ptr + off);
     off = align_up(off + p.M_pad * p.nseg * (int64_t)kCap * (int64_t)sizeof(Cand), 256);
     w.fb_rows = reinterpret_cast<uint32_t *>(ptr + off);
+    off = align_up(off + p.M * 4, 256);
+    w.fb_rows2 = reinterpret_cast<uint32_t *>(ptr + off);
     off = align_up(off + p.M * 4, 256);
     w.st_rows = reinterpret_cast<uint32_t *>(ptr + off);
     off = align_up(off + p.M * 4, 256);
@@ -1375,6 +1378,128 @@ __device__ __forceinline__ float prefilter_score_smem(const float (&x)[G], const
 
 constexpr int kMaxChunks = 64;   // surviving chunks one row may carry into the rescoring (else: exact scan)
 
+// ---- pruned exact scan of a row the search could not certify ----------------------------------------------------
+// Such rows are the sharp ones (a variance of ~1e-5 or less in some dimension: the reference's extension-test
+// latents, std = |randn|): their fp16 / split-precision windows are wider than their score gaps.  But a sharp
+// dimension k* prunes by itself: t_k*(x) = -(x - mu)^2 / (2 v) + beta x^2 / 2 + const falls off so fast that only
+// codewords with x_k* within a few sigma of mu_k* can win.  The codebook is kept sorted per dimension
+// (gq_codebook::sort_val / sort_idx); one warp walks outward from mu_k* in that order, 16 candidates per side
+// and step, scoring each in the reference's exact op order (lane = candidate; lowest index wins ties), and stops a
+// side as soon as an upper bound on every unvisited candidate's score there -- the k* term at the next distance
+// plus, for every other dimension, the maximum of its term over the codebook's range of that coordinate, evaluated
+// in double, with slack for the fp32 rounding of the exact evaluation -- falls strictly below the best exact score
+// seen.  Rigorous, so the result is the reference argmax; rows that do not prune within kPrunedBudget candidates (or
+// hold non-finite values) return false and take the sliced full scan.
+constexpr int kPrunedBudget = 8192;
+
+template <int G>
+__device__ bool pruned_exact_row(int64_t r, const float *__restrict__ mu, const float *__restrict__ std,
+                                 const float *__restrict__ lstd, const float *__restrict__ cb, const float *__restrict__ nlpb,
+                                 const float *__restrict__ meta, const float *__restrict__ sort_val,
+                                 const uint32_t *__restrict__ sort_idx, int64_t N, float beta, int lane,
+                                 int64_t *__restrict__ idx_out, float *__restrict__ zhat_out)
+{
+    float m[G], den[G], ls[G];
+    int ks = 0;
+    float smin = CUDART_INF_F;
+    double crest = 0.0, cabs = 0.0, c_ks = 0.0, inv2v_ks = 0.0;
+    {
+        float sd[G];
+        load_row<G>(mu + r * G, m);
+        load_row<G>(std + r * G, sd);
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            den[k] = __fmul_rn(2.0f, __fmul_rn(sd[k], sd[k]));
+            ls[k] = lstd ? __ldg(lstd + r * G + k) : logf(sd[k]);
+            if (sd[k] < smin) { smin = sd[k]; ks = k; }
+        }
+        const double c0 = (double)GQ_C0F;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const double v = (double)sd[k] * (double)sd[k];
+            const double cst = -(double)ls[k] - c0 + (double)beta * c0;
+            if (k == ks) {
+                inv2v_ks = 0.5 / v;
+                c_ks = 0.5 * (double)beta * (double)meta[2 + k] + cst;       // beta x^2 / 2 <= beta max x_k^2 / 2
+                cabs += fabs(c_ks);
+            } else {
+                // max over |x| <= X of  a x^2 + b x - mu^2 / (2 v),  a = beta/2 - 1/(2v),  b = mu / v
+                const double a = 0.5 * (double)beta - 0.5 / v, bb = (double)m[k] / v, X = (double)meta[2 + G + k];
+                double fmx;
+                if (a < 0.0) {
+                    double xs = -bb / (2.0 * a);
+                    xs = xs > X ? X : (xs < -X ? -X : xs);
+                    fmx = a * xs * xs + bb * xs;
+                } else {
+                    fmx = a * X * X + fabs(bb) * X;
+                }
+                const double term = fmx - 0.5 * (double)m[k] * (double)m[k] / v + cst;
+                crest += term;
+                cabs += fabs(fmx) + 0.5 * (double)m[k] * (double)m[k] / v + fabs(cst);
+            }
+        }
+    }
+    // everything an unvisited candidate can score beyond its k* distance term, plus slack for the fp32 evaluation
+    const double cbound = crest + c_ks + 1e-5 * cabs + 1e-3;
+    const float *sv = sort_val + (int64_t)ks * N;
+    const uint32_t *si = sort_idx + (int64_t)ks * N;
+    const float mk = m[ks];
+    int64_t lo = 0, hi = N;          // lower_bound(sv, mk)
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(sv + mid) < mk) lo = mid + 1; else hi = mid;
+    }
+    int64_t left = lo - 1, right = lo;   // next unvisited position on either side
+    bool open_l = left >= 0, open_r = right < N;
+    float best = -CUDART_INF_F;
+    int best_idx = 0x7fffffff;
+    int visited = 0;
+    if (!(mk == mk) || !(cbound == cbound)) return false;      // NaN: the sliced scan decides
+    while (open_l || open_r) {
+        const bool is_l = lane < 16;
+        const int64_t pos = is_l ? left - lane : right + (lane - 16);
+        if ((is_l ? open_l : open_r) && pos >= 0 && pos < N) {
+            const int64_t n = (int64_t)__ldg(si + pos);
+            float x[G], nb[G];
+            load_row<G>(cb + n * G, x);
+            load_row<G>(nlpb + n * G, nb);
+            const float sc = score_exact<G>(x, nb, m, den, ls);
+            if (sc > best || (sc == best && (int)n < best_idx)) { best = sc; best_idx = (int)n; }
+        }
+        if (open_l) left -= 16;
+        if (open_r) right += 16;
+        visited += 32;
+        float gb = best;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) gb = fmaxf(gb, __shfl_xor_sync(0xffffffffu, gb, off));
+        if (open_l) {
+            if (left < 0) open_l = false;
+            else {
+                const double d = (double)mk - (double)__ldg(sv + left);
+                if (-(d * d) * inv2v_ks * (1.0 - 1.0 / 262144.0) + cbound < (double)gb) open_l = false;
+            }
+        }
+        if (open_r) {
+            if (right >= N) open_r = false;
+            else {
+                const double d = (double)__ldg(sv + right) - (double)mk;
+                if (-(d * d) * inv2v_ks * (1.0 - 1.0 / 262144.0) + cbound < (double)gb) open_r = false;
+            }
+        }
+        if (visited >= kPrunedBudget && (open_l || open_r)) return false;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
+        if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+    }
+    if (best_idx == 0x7fffffff || !(best > -CUDART_INF_F)) return false;
+    if (lane == 0) idx_out[r] = (int64_t)best_idx;
+    if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
+    return true;
+}
+
 // Rows whose fp32 prefilter left more than one contender (a few percent): one warp per listed row
 // re-reads the segment summaries and scores every codeword of the surviving chunks (lane = codeword)
 // in the reference's exact fp32 op order; first-max tie-break.  Runs after rescore_kernel, before the
@@ -1387,11 +1512,22 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
               const uint32_t *__restrict__ rows, const uint32_t *__restrict__ row_chunks, const uint32_t *__restrict__ nrows, int64_t N, int tiles,
               int steps_per_cta, int nseg, int unit_rows, int64_t *__restrict__ idx_out, float *__restrict__ zhat_out,
               uint32_t *__restrict__ fb_rows, uint32_t *__restrict__ fb_count, unsigned long long *__restrict__ fb_keys,
-              float win_rel)
+              float win_rel, const uint32_t *__restrict__ pr_rows, const uint32_t *__restrict__ pr_count,
+              const float *__restrict__ meta, const float *__restrict__ sort_val, const uint32_t *__restrict__ sort_idx, float beta)
 {
     const int lane = threadIdx.x & 31;
     pdl_wait();
-    const uint32_t total = *nrows;
+    // Second job of this kernel: the rows the rescoring kernel could not certify (pr_rows, complete before this
+    // kernel starts) take the pruned exact scan; what that cannot decide goes on to the sliced full scan (fb_rows).
+    const uint32_t npr = *pr_count;
+    const uint32_t total = *nrows;      // (both counters are fetched together: one round trip at the head of the kernel)
+    {
+        for (uint32_t it = blockIdx.x * 4 + (threadIdx.x >> 5); it < npr; it += gridDim.x * 4) {
+            const int64_t r = (int64_t)pr_rows[it];
+            const bool done = pruned_exact_row<G>(r, mu, std, lstd, cb, nlpb, meta, sort_val, sort_idx, N, beta, lane, idx_out, zhat_out);
+            if (!done && lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
+        }
+    }
     for (uint32_t it = blockIdx.x * 4 + (threadIdx.x >> 5); it < total; it += gridDim.x * 4) {
         const uint32_t entry = rows[it];
         const bool full = (entry & 0x80000000u) != 0u;   // a segment kept more than kSurv survivors: walk its full list
@@ -1910,7 +2046,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
         int sblocks = (int)imin((M + 3) / 4, (int64_t)device_sm_count() * 8);
         launch_chained(settle_kernel<G>, dim3(sblocks), dim3(128), 0, stream, mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.seg,
                        w.cand, w.rec_cnt, w.st_rows, w.st_chunks, w.counters + 1, cb->N, p.tiles, p.steps_per_cta, p.nseg, p.unit_rows, idx, zhat,
-                       w.fb_rows, w.counters, w.fb_keys, win_rel);
+                       w.fb_rows2, w.counters + 2, w.fb_keys, win_rel, w.fb_rows, w.counters, cb->meta, cb->sort_val, cb->sort_idx, cb->beta);
     }
     rc = check_launch("settle_kernel");
     if (rc) return rc;
@@ -1918,7 +2054,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
 
     // exact scan over the rows the search could not certify (device-side count, no host sync),
     // sliced over the codebook so that a handful of rows still spreads over the whole GPU
-    return launch_exact_sliced(cb, mu, std, lstd, M, w.fb_rows, w.counters, w.fb_keys, w.counters + 64, idx, zhat, stream);
+    return launch_exact_sliced(cb, mu, std, lstd, M, w.fb_rows2, w.counters + 2, w.fb_keys, w.counters + 64, idx, zhat, stream);
 }
 
 // Debug/diagnostic path (tests only): runs row prep + the search with the DUMP epilogue and
