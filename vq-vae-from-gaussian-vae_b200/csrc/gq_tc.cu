@@ -1393,7 +1393,7 @@ constexpr int kMaxChunks = 64;   // surviving chunks one row may carry into the 
 constexpr int kPrunedBudget = 8192;
 
 template <int G>
-__device__ bool pruned_exact_row(int64_t r, const float *__restrict__ mu, const float *__restrict__ std,
+__device__ __noinline__ bool pruned_exact_row(int64_t r, const float *__restrict__ mu, const float *__restrict__ std,
                                  const float *__restrict__ lstd, const float *__restrict__ cb, const float *__restrict__ nlpb,
                                  const float *__restrict__ meta, const float *__restrict__ sort_val,
                                  const uint32_t *__restrict__ sort_idx, int64_t N, float beta, int lane,
@@ -1504,6 +1504,98 @@ __device__ bool pruned_exact_row(int64_t r, const float *__restrict__ mu, const 
 // re-reads the segment summaries and scores every codeword of the surviving chunks (lane = codeword)
 // in the reference's exact fp32 op order; first-max tie-break.  Runs after rescore_kernel, before the
 // exact-scan fallback (to which it can still defer a row with non-finite scores).
+// One row whose fp32 prefilter left more than one contender: score every codeword of its surviving chunks (lane =
+// codeword) in the reference's exact fp32 op order, first-max tie-break, and write the result.  `my_word`: lane 0 holds
+// the number of listed chunks (<= 7, else the summaries / full record lists are walked), lanes 1..7 the chunk ids.
+// Returns false when no finite score was found (the caller sends the row on).
+template <int G>
+__device__ __forceinline__ bool settle_row(int64_t r, bool full, uint32_t my_word, int lane,
+                                           const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
+                                           const float *__restrict__ cb, const float *__restrict__ nlpb, const float *__restrict__ wrow,
+                                           const SegHdr *__restrict__ seg_hdr, const Cand *__restrict__ cand,
+                                           const uint32_t *__restrict__ rec_cnt, int64_t N, int tiles, int steps_per_cta, int nseg,
+                                           int unit_rows, float win_rel, int64_t *__restrict__ idx_out, float *__restrict__ zhat_out)
+{
+    const uint32_t n_listed = __shfl_sync(0xffffffffu, my_word, 0);
+    float m[G], den[G], ls[G];
+    load_row<G>(mu + r * G, m);
+    {
+        float sd[G];
+        load_row<G>(std + r * G, sd);
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            den[k] = __fmul_rn(2.0f, __fmul_rn(sd[k], sd[k]));
+            ls[k] = lstd ? __ldg(lstd + r * G + k) : logf(sd[k]);
+        }
+    }
+    float best = -CUDART_INF_F;
+    int best_idx = 0x7fffffff;
+    auto score_chunk = [&](uint32_t chunk) {
+        const int64_t n = (int64_t)chunk * kChunk + lane;
+        if (lane < kChunk && n < N) {
+            float x[G], nb[G];
+            load_row<G>(cb + n * G, x);
+            load_row<G>(nlpb + n * G, nb);
+            const float sc = score_exact<G>(x, nb, m, den, ls);
+            if (sc > best || (sc == best && (int)n < best_idx)) { best = sc; best_idx = (int)n; }
+        }
+    };
+    if (!full && n_listed <= 7u) {
+        for (uint32_t c = 0; c < n_listed; ++c) score_chunk(__shfl_sync(0xffffffffu, my_word, (int)c + 1));
+    } else {
+        // Walk the summaries (or, for rows flagged `full`, the complete record lists) with the warp in
+        // parallel: lane s takes segment s for the running maxima, lane i takes record i of a list
+        // (kCap = 32 = one record per lane, one coalesced load per segment); the survivors' chunk ids
+        // are then broadcast one by one.  A single lane walking the lists cost 15 us per launch.
+        const uint32_t s0 = (uint32_t)(r / unit_rows) * (uint32_t)tiles;
+        const int npieces = kHalves * ((int)((s0 + (uint32_t)tiles - 1u) / (uint32_t)steps_per_cta) - (int)(s0 / (uint32_t)steps_per_cta) + 1);
+        float gmax = -CUDART_INF_F;
+        for (int s = lane; s < npieces; s += 32) gmax = fmaxf(gmax, seg_hdr[r * nseg + s].runmax);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+        const float thr = win_thr(gmax, wrow[r], win_rel);
+        static_assert(kCap == 32, "one record per lane");
+        // eight segments per trip, their (independent) loads issued before any is consumed: with many
+        // segments per row (small M: a unit is spread over up to 148 CTAs) this walk is the whole kernel
+        constexpr int kU = 8;
+        for (int sb = 0; sb < npieces; sb += kU) {
+            Cand c[kU];
+            uint32_t cnt[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int s = sb + u;
+                c[u] = Cand{-CUDART_INF_F, 0u};
+                cnt[u] = 0u;
+                if (s < npieces) {
+                    const SegHdr *h = &seg_hdr[r * nseg + s];
+                    const Cand *list = full ? cand + (r * nseg + s) * (int64_t)kCap : h->surv;
+                    cnt[u] = full ? rec_cnt[r * nseg + s] : h->cnt;   // <= kCap resp. <= kSurv by construction
+                    if (lane < (full ? kCap : kSurv)) c[u] = list[lane];   // in bounds; masked by cnt below
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                unsigned mask = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt[u] && c[u].score >= thr);
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    score_chunk(__shfl_sync(0xffffffffu, c[u].idx, src));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
+        if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+    }
+    if (best_idx == 0x7fffffff || !(best > -CUDART_INF_F)) return false;
+    if (lane == 0) idx_out[r] = (int64_t)best_idx;
+    if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
+    return true;
+}
+
 template <int G>
 __global__ void __launch_bounds__(128)
 settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const float *__restrict__ lstd,
@@ -1535,86 +1627,9 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
         // rescore_kernel attached the row's surviving chunks (lane i holds word i of the 8-word entry):
         // one load instead of a walk over the segment summaries
         const uint32_t my_word = lane < 8 ? __ldg(row_chunks + (int64_t)it * 8 + lane) : 0u;
-        const uint32_t n_listed = __shfl_sync(0xffffffffu, my_word, 0);
-        float m[G], den[G], ls[G];
-        load_row<G>(mu + r * G, m);
-        {
-            float sd[G];
-            load_row<G>(std + r * G, sd);
-#pragma unroll
-            for (int k = 0; k < G; ++k) {
-                den[k] = __fmul_rn(2.0f, __fmul_rn(sd[k], sd[k]));
-                ls[k] = lstd ? __ldg(lstd + r * G + k) : logf(sd[k]);
-            }
-        }
-        float best = -CUDART_INF_F;
-        int best_idx = 0x7fffffff;
-        auto score_chunk = [&](uint32_t chunk) {
-            const int64_t n = (int64_t)chunk * kChunk + lane;
-            if (lane < kChunk && n < N) {
-                float x[G], nb[G];
-                load_row<G>(cb + n * G, x);
-                load_row<G>(nlpb + n * G, nb);
-                const float sc = score_exact<G>(x, nb, m, den, ls);
-                if (sc > best || (sc == best && (int)n < best_idx)) { best = sc; best_idx = (int)n; }
-            }
-        };
-        if (!full && n_listed <= 7u) {
-            for (uint32_t c = 0; c < n_listed; ++c) score_chunk(__shfl_sync(0xffffffffu, my_word, (int)c + 1));
-        } else {
-            // Walk the summaries (or, for rows flagged `full`, the complete record lists) with the warp in
-            // parallel: lane s takes segment s for the running maxima, lane i takes record i of a list
-            // (kCap = 32 = one record per lane, one coalesced load per segment); the survivors' chunk ids
-            // are then broadcast one by one.  A single lane walking the lists cost 15 us per launch.
-            const uint32_t s0 = (uint32_t)(r / unit_rows) * (uint32_t)tiles;
-            const int npieces = kHalves * ((int)((s0 + (uint32_t)tiles - 1u) / (uint32_t)steps_per_cta) - (int)(s0 / (uint32_t)steps_per_cta) + 1);
-            float gmax = -CUDART_INF_F;
-            for (int s = lane; s < npieces; s += 32) gmax = fmaxf(gmax, seg_hdr[r * nseg + s].runmax);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
-            const float thr = win_thr(gmax, wrow[r], win_rel);
-            static_assert(kCap == 32, "one record per lane");
-            // eight segments per trip, their (independent) loads issued before any is consumed: with many
-            // segments per row (small M: a unit is spread over up to 148 CTAs) this walk is the whole kernel
-            constexpr int kU = 8;
-            for (int sb = 0; sb < npieces; sb += kU) {
-                Cand c[kU];
-                uint32_t cnt[kU];
-#pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const int s = sb + u;
-                    c[u] = Cand{-CUDART_INF_F, 0u};
-                    cnt[u] = 0u;
-                    if (s < npieces) {
-                        const SegHdr *h = &seg_hdr[r * nseg + s];
-                        const Cand *list = full ? cand + (r * nseg + s) * (int64_t)kCap : h->surv;
-                        cnt[u] = full ? rec_cnt[r * nseg + s] : h->cnt;   // <= kCap resp. <= kSurv by construction
-                        if (lane < (full ? kCap : kSurv)) c[u] = list[lane];   // in bounds; masked by cnt below
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    unsigned mask = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt[u] && c[u].score >= thr);
-                    while (mask) {
-                        const int src = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        score_chunk(__shfl_sync(0xffffffffu, c[u].idx, src));
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
-            if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
-        }
-        if (best_idx == 0x7fffffff || !(best > -CUDART_INF_F)) {
-            if (lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
-        } else {
-            if (lane == 0) idx_out[r] = (int64_t)best_idx;
-            if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
-        }
+        const bool done = settle_row<G>(r, full, my_word, lane, mu, std, lstd, cb, nlpb, wrow, seg_hdr, cand, rec_cnt, N, tiles,
+                                        steps_per_cta, nseg, unit_rows, win_rel, idx_out, zhat_out);
+        if (!done && lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
     }
 }
 
@@ -1806,7 +1821,9 @@ rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std,
                     int64_t *__restrict__ idx_out, float *__restrict__ zhat_out, uint32_t *__restrict__ fb_rows,
                     uint32_t *__restrict__ fb_count, uint32_t *__restrict__ settle_rows, uint32_t *__restrict__ settle_chunks,
                     uint32_t *__restrict__ settle_count, const uint32_t *__restrict__ rec_cnt,
-                    unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats, float win_rel)
+                    unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats, float win_rel,
+                    const float *__restrict__ nlpb, const Cand *__restrict__ cand, int tiles, int steps_per_cta, int unit_rows,
+                    const float *__restrict__ meta, const float *__restrict__ sort_val, const uint32_t *__restrict__ sort_idx)
 {
     __shared__ __align__(16) float s_par[kRescoreWarps][2][G < 4 ? 4 : G];   // -mu, -1/den of the warp's row
     __shared__ uint32_t s_chunks[kRescoreWarps][kMaxChunks];
@@ -1950,24 +1967,24 @@ rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std,
                 else verdict = 1;   // several codewords within the prefilter margin: exact op order decides
             }
         }
+        // Plans with this many segments are small calls (one image), where every dependent launch is a fixed cost:
+        // the row is finished HERE -- ambiguous rows are settled in the exact op order, uncertified rows take the pruned
+        // exact scan -- and only what neither decides goes on to the sliced full scan.  No settle_kernel launch.
         if (verdict == 0) {
             if (lane == 0) idx_out[r] = (int64_t)best_idx;
             if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
-        } else if (verdict == 3) {
-            if (lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
         } else {
-            uint32_t slot = 0;
-            if (lane == 0) {
-                slot = atomicAdd(settle_count, 1u);
-                settle_rows[slot] = (uint32_t)r | (verdict == 2 ? 0x80000000u : 0u);
-            }
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (lane < 8) {
+            bool done;
+            if (verdict == 3) {
+                done = pruned_exact_row<G>(r, mu, std, lstd, cb, nlpb, meta, sort_val, sort_idx, N, beta, lane, idx_out, zhat_out);
+            } else {
                 const bool listed = verdict == 1 && nchunks <= 7;
                 uint32_t v = listed ? (uint32_t)nchunks : 0xffffffffu;
-                if (lane > 0) v = (listed && lane - 1 < nchunks) ? s_chunks[wib][lane - 1] : 0u;
-                settle_chunks[(int64_t)slot * 8 + lane] = v;
+                if (lane > 0) v = (listed && lane < 8 && lane - 1 < nchunks) ? s_chunks[wib][lane - 1] : 0u;
+                done = settle_row<G>(r, verdict == 2, v, lane, mu, std, lstd, cb, nlpb, wrow, seg_hdr, cand, rec_cnt, N, tiles,
+                                     steps_per_cta, nseg, unit_rows, win_rel, idx_out, zhat_out);
             }
+            if (!done && lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
         }
         __syncwarp();   // s_chunks / s_par are rewritten for the next row
         st_rows += 1;
@@ -2033,24 +2050,32 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
     {
         int64_t need = (M + kRescoreWarps - 1) / kRescoreWarps;
         int blocks = (int)imin(need, (int64_t)device_sm_count() * 8);
-        if (p.nseg > 8)
+        if (p.nseg > 8) {
+            // small calls: rescore_many_kernel finishes its rows itself (settlement and pruned scan inline);
+            // its leftovers go straight to the sliced scan's list
             launch_chained(rescore_many_kernel<G>, dim3(blocks), dim3(kRescoreWarps * 32), 0, stream,
-                           mu, std, lstd, cb->cb, w.wrow, w.margin, w.seg, M, cb->N, p.nseg, cb->beta, idx, zhat, w.fb_rows,
-                           w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats, win_rel);
-        else
+                           mu, std, lstd, cb->cb, w.wrow, w.margin, w.seg, M, cb->N, p.nseg, cb->beta, idx, zhat, w.fb_rows2,
+                           w.counters + 2, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats, win_rel,
+                           cb->nlpb, w.cand, p.tiles, p.steps_per_cta, p.unit_rows, cb->meta, cb->sort_val, cb->sort_idx);
+            rc = check_launch("rescore_many_kernel");
+            if (rc) return rc;
+            count_launch(1);
+        } else {
             launch_chained(rescore_kernel<G>, dim3(blocks), dim3(kRescoreWarps * 32), 0, stream,
                            mu, std, lstd, cb->cb, w.wrow, w.margin, w.seg, M, cb->N, p.nseg, cb->beta, idx, zhat, w.fb_rows,
                            w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats, win_rel);
-        rc = check_launch("rescore_kernel");
-        if (rc) return rc;
-        int sblocks = (int)imin((M + 3) / 4, (int64_t)device_sm_count() * 8);
-        launch_chained(settle_kernel<G>, dim3(sblocks), dim3(128), 0, stream, mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.seg,
-                       w.cand, w.rec_cnt, w.st_rows, w.st_chunks, w.counters + 1, cb->N, p.tiles, p.steps_per_cta, p.nseg, p.unit_rows, idx, zhat,
-                       w.fb_rows2, w.counters + 2, w.fb_keys, win_rel, w.fb_rows, w.counters, cb->meta, cb->sort_val, cb->sort_idx, cb->beta);
+            rc = check_launch("rescore_kernel");
+            if (rc) return rc;
+            int sblocks = (int)imin((M + 3) / 4, (int64_t)device_sm_count() * 8);
+            launch_chained(settle_kernel<G>, dim3(sblocks), dim3(128), 0, stream, mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.seg,
+                           w.cand, w.rec_cnt, w.st_rows, w.st_chunks, w.counters + 1, cb->N, p.tiles, p.steps_per_cta, p.nseg, p.unit_rows, idx, zhat,
+                           w.fb_rows2, w.counters + 2, w.fb_keys, win_rel, w.fb_rows, w.counters, cb->meta, cb->sort_val, cb->sort_idx, cb->beta);
+            rc = check_launch("settle_kernel");
+            if (rc) return rc;
+            count_launch(2);
+        }
     }
-    rc = check_launch("settle_kernel");
-    if (rc) return rc;
-    count_launch(3);
+    count_launch(1);   // the search kernel
 
     // exact scan over the rows the search could not certify (device-side count, no host sync),
     // sliced over the codebook so that a handful of rows still spreads over the whole GPU
