@@ -526,6 +526,22 @@ def leg_configs(ctx):
         out["configs[3]"] = {"error": repr(e)}
     torch.cuda.empty_cache()
 
+    # ---- configs[0] shape on the GPU: one 256-px image (1024 rows), the launch-bound end of the path ----
+    try:
+        reg1 = gq_b200.GaussianQuantRegularizer(format="bchw", n_samples=N_SAMPLES, group=GROUP, backend="cuda").to(dev).eval()
+        z1 = [synth_latents(1, 700 + i).to(dev) for i in range(8)]
+        ms_eager = ctx.time_loop(lambda k: reg1(z1[k % 8]), 200, warm=10, bracket=False)
+        run = reg1.graphed_eval(z1[0])
+        ms_graph = ctx.time_loop(lambda k: run(z1[k % 8]), 200, warm=10, bracket=False)
+        out["configs[0]_single_image"] = {"workload": "one 256-px image: z[1,32,32,32] -> 1024 rows x 65536x16 codebook, module eval forward",
+                                          "eager_us_per_call": ms_eager * 1e3, "graph_replay_us_per_call": ms_graph * 1e3,
+                                          "note": "back-to-back calls, CUDA events; graph_replay = GaussianQuantRegularizer.graphed_eval "
+                                                  "(same indices, same RNG stream as the eager call)"}
+        del reg1, run, z1
+    except Exception as e:  # noqa: BLE001
+        out["configs[0]_single_image"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+
     # ---- dequant (gaussian.py:162-178) ----
     try:
         reg = gq_b200.GaussianQuantRegularizer(format="bchw", n_samples=N_SAMPLES, group=GROUP, backend="cuda").to(dev).eval()

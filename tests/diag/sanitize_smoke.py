@@ -25,6 +25,23 @@ for (N,g,M) in ((1000,16,300),(4096,4,700),(4096,8,300)):
     cb.set_mode("robust")
     idx,zh=gq_b200.quantize_rows(cb, mu.to(dev), std.to(dev), std.log().to(dev))
     print(" robust mismatch",int((idx.cpu().numpy()!=o).sum()))
+# sharp rows (pruned exact scan inside settle_kernel), one NaN row (sliced full scan), and a many-segment plan
+# (small M against a larger codebook: rescore_many_kernel settles and prunes inline)
+for (N,g,M) in ((4096,16,200),(16384,16,64)):
+    cbn,nlp=host_codebook(N,g)
+    cb=gq_b200.Codebook(torch.from_numpy(cbn).to(dev), torch.from_numpy(nlp).to(dev), 1.0)
+    gen=torch.Generator().manual_seed(2)
+    mu=torch.randn(M,g,generator=gen); std=torch.abs(torch.randn(M,g,generator=gen)).clamp_min(1e-4)
+    std[::7,3]=2e-4
+    o,_,_,_=oracle.quantize(mu.numpy(),std.numpy(),std.log().numpy(),cbn,nlp)
+    for mode in ("fast","robust"):
+        cb.set_mode(mode)
+        st=torch.zeros(8,dtype=torch.int32,device=dev)
+        idx,zh=gq_b200.quantize_rows(cb, mu.to(dev), std.to(dev), std.log().to(dev), stats=st)
+        print(N,g,M,mode,"stress mismatch",int((idx.cpu().numpy()!=o).sum()),"uncertified rows",int(st[2]))
+    mu2=mu.clone(); mu2[5,2]=float("nan")
+    idx,zh=gq_b200.quantize_rows(cb, mu2.to(dev), std.to(dev), std.log().to(dev))
+    print(" nan row index", int(idx[5]))
 # latent path + KL + tokens
 reg=gq_b200.GaussianQuantRegularizer(format="bchw", n_samples=4096, group=16, backend="cuda").cuda().eval()
 z=torch.randn(2,32,8,8,device=dev)*0.5
