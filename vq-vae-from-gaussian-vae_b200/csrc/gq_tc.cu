@@ -10,26 +10,32 @@
 //                         window W_r bounding twice the worst-case |fp16 tensor-core score -
 //                         reference fp32 score| gap, and the (much smaller) margin of the fp32
 //                         prefilter used by the rescoring kernel.
-//   2. quantize_tc_kernel persistent, warp-specialised, 640 threads: a producer warp streams the
-//                         prepared [x^2 | x] codebook image through an 8-slot shared-memory ring
-//                         (bulk async copies, TMA engine); one issuer warp per 128-row block
-//                         issues tcgen05.mma (fp16 x fp16 -> fp32, M=128, N=128, K=2g, both
-//                         operands from shared memory: the row operand is written there once
-//                         per work unit) into that row block's two private TMEM accumulator
-//                         stages (4 x 128 columns = all of tensor memory); sixteen epilogue
-//                         warps pull 32x64 half tiles with tcgen05.ld, hand the stage back
-//                         before any math, and keep a running row maximum with FMNMX3; a
-//                         32-column chunk whose maximum comes within W_r of the running
-//                         maximum is recorded as (max, chunk id); per-piece survivors are
-//                         compacted into a 64-byte segment summary.
-//   3. rescore_kernel     one warp per row: drop chunk records below (final max - W_r), score
-//                         the 32 codewords of every surviving chunk (lane = codeword) with an
-//                         fp32 FMA form; if exactly one codeword lies within the prefilter
-//                         margin of the best it is the answer, otherwise the row goes to
+//   2. quantize_tc_kernel persistent, warp-specialised, 608 threads: a producer warp streams the
+//                         prepared [x^2 | x] codebook image through a shared-memory ring (bulk
+//                         async copies, TMA engine); one issuer warp per 128-row block issues
+//                         tcgen05.mma (fp16 x fp16, M=128, N=128, K=2g, both operands from shared
+//                         memory: the row operand is written there once per work unit) into that
+//                         row block's two private TMEM accumulator stages (4 x 128 columns = all of
+//                         tensor memory).  Plain fp16 images of groups 8 / 16 (the headline): FP16
+//                         accumulators, read back packed (tcgen05.ld ... pack::16b, two scores per
+//                         register) by epilogue warps that own one stage each and keep the running
+//                         row maximum with packed three-input fp16 maxima (VHMNMX).  Split-precision
+//                         images: fp32 accumulators, 32x64 half tiles, FMNMX3.  Either way the stage
+//                         is handed back before any math, a 32-codeword chunk whose maximum comes
+//                         within the row's window of the running maximum is recorded as (max,
+//                         chunk id), and per-piece survivors are compacted into a 64-byte summary.
+//                         (quantize_tc16_kernel: experimental TS-form variant, -DGQ_ACC16_TS=1.)
+//   3. rescore_kernel     one warp per row: drop chunk records below the window under the final
+//                         maximum, score the 32 codewords of every surviving chunk (lane =
+//                         codeword) with an fp32 FMA form; if exactly one codeword lies within the
+//                         prefilter margin of the best it is the answer, otherwise the row goes to
 //   4. settle_kernel      (a few percent of the rows) which re-scores the contenders in the
-//                         reference's exact fp32 op order (first-max tie-break).  Rows whose
-//                         window is too wide or that contain non-finite values go to
-//   5. exact_sliced_kernel (gq_kernels.cu), an exact-order scan, through a device-side row list.
+//                         reference's exact fp32 op order (first-max tie-break).  Rows the search
+//                         cannot certify (window too wide, lists overflowed, non-finite values) take
+//                         the pruned exact scan along their sharpest dimension in the same kernel
+//                         (pruned_exact_row); what that cannot decide goes to
+//   5. exact_sliced_kernel (gq_kernels.cu), an exact-order full scan, through a device-side row list.
+//      Small calls (many segments per row) finish steps 3-4 inside rescore_many_kernel.
 //
 // Why the result is exactly the reference argmax: with E_r >= |G~[n]/s - (S_ref[n] - Q_r)| for
 // all n (Q_r constant in n), the reference argmax n* satisfies
