@@ -117,6 +117,14 @@ constexpr int kCap = 32;             // chunk records per (row, segment)
 constexpr int kChunk = GQ_CHUNK;     // columns per recorded chunk (32 or 16); the rescoring kernels gather kChunk codewords per record
 static_assert(kChunk == 32 || kChunk == 16, "chunk width");
 constexpr int kMinStepsPerCta = 8;
+// rescore_kernel settling / pruning its rows itself instead of handing them to settle_kernel (one launch less) was
+// measured at batch 64: 0.339 ms per step against 0.292 -- the rare rows, run out of line under the 64-register cap,
+// turn their warps into stragglers of a kernel in which every warp walks ~14 rows.  Off; small calls
+// (rescore_many_kernel) do finish their rows inline, where the launch is what costs.
+#ifndef GQ_RESCORE_FINISHES
+#define GQ_RESCORE_FINISHES 0
+#endif
+constexpr bool kRescoreFinishes = GQ_RESCORE_FINISHES != 0;
 #ifndef GQ_FRONTEND_X4
 #define GQ_FRONTEND_X4 1     // group 16, plain image: four lanes per row in the fused front-end (0: one thread per row)
 #endif
@@ -1639,6 +1647,30 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
     }
 }
 
+// What a rescoring kernel needs to FINISH a row itself (exact-order settlement, pruned exact scan) instead of
+// handing it to settle_kernel: both are rare paths (under 1 % of the rows on trained latents), called out of line so
+// that their register appetite (they spill under the 64-register cap) stays out of the main loop.
+struct TailArgs {
+    const float *nlpb;
+    const Cand *cand;
+    int tiles, steps_per_cta, unit_rows;
+    const float *meta;
+    const float *sort_val;
+    const uint32_t *sort_idx;
+    uint32_t *fb2_rows;      // rows left for the sliced full scan
+    uint32_t *fb2_count;
+};
+
+template <int G>
+__device__ __noinline__ bool settle_row_call(int64_t r, bool full, uint32_t my_word, int lane, const float *mu, const float *std,
+                                             const float *lstd, const float *cb, const float *wrow, const SegHdr *seg_hdr,
+                                             const uint32_t *rec_cnt, int64_t N, int nseg, float win_rel, int64_t *idx_out,
+                                             float *zhat_out, const TailArgs &ta)
+{
+    return settle_row<G>(r, full, my_word, lane, mu, std, lstd, cb, ta.nlpb, wrow, seg_hdr, ta.cand, rec_cnt, N, ta.tiles,
+                         ta.steps_per_cta, nseg, ta.unit_rows, win_rel, idx_out, zhat_out);
+}
+
 struct RowIn { float w, margin, pm, ps; uint4 q; };
 
 template <int G>
@@ -1686,7 +1718,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                int64_t *__restrict__ idx_out, float *__restrict__ zhat_out, uint32_t *__restrict__ fb_rows,
                uint32_t *__restrict__ fb_count, uint32_t *__restrict__ settle_rows, uint32_t *__restrict__ settle_chunks,
                uint32_t *__restrict__ settle_count, const uint32_t *__restrict__ rec_cnt,
-               unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats, float win_rel)
+               unsigned long long *__restrict__ fb_keys, uint32_t *__restrict__ stats, float win_rel, const TailArgs ta)
 {
     __shared__ __align__(16) float s_par[kRescoreWarps][2][G < 4 ? 4 : G];   // -mu, -1/den of the warp's row
     __shared__ uint32_t s_chunks[kRescoreWarps][kMaxChunks];
@@ -1778,6 +1810,21 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
             if (verdict == 0) {
                 if (lane == 0) idx_out[r] = (int64_t)best_idx;
                 if (zhat_out && lane < G) zhat_out[r * G + lane] = __ldg(cb + (int64_t)best_idx * G + lane);
+            } else if (kRescoreFinishes) {
+                // finish the row here (no settle_kernel launch): exact-order settlement of the listed chunks, resp. the
+                // pruned exact scan for a row the search could not certify; leftovers go to the sliced full scan
+                bool done;
+                if (verdict == 3) {
+                    done = pruned_exact_row<G>(r, mu, std, lstd, cb, ta.nlpb, ta.meta, ta.sort_val, ta.sort_idx, N, beta, lane, idx_out, zhat_out);
+                } else {
+                    const bool listed = verdict == 1 && n_chunks_row <= 7;
+                    uint32_t v = listed ? (uint32_t)n_chunks_row : 0xffffffffu;
+                    if (lane > 0) v = (listed && lane < 8 && lane - 1 < n_chunks_row) ? s_chunks[wib][lane - 1] : 0u;
+                    done = settle_row_call<G>(r, verdict == 2, v, lane, mu, std, lstd, cb, wrow, seg_hdr, rec_cnt, N, nseg, win_rel,
+                                              idx_out, zhat_out, ta);
+                }
+                if (!done && lane == 0) { fb_keys[r] = 0ull; ta.fb2_rows[atomicAdd(ta.fb2_count, 1u)] = (uint32_t)r; }
+                __syncwarp();
             } else if (verdict == 3) {
                 if (lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
             } else {
@@ -2067,11 +2114,13 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
             if (rc) return rc;
             count_launch(1);
         } else {
+            const TailArgs ta{cb->nlpb, w.cand, p.tiles, p.steps_per_cta, p.unit_rows, cb->meta, cb->sort_val, cb->sort_idx, w.fb_rows2, w.counters + 2};
             launch_chained(rescore_kernel<G>, dim3(blocks), dim3(kRescoreWarps * 32), 0, stream,
                            mu, std, lstd, cb->cb, w.wrow, w.margin, w.seg, M, cb->N, p.nseg, cb->beta, idx, zhat, w.fb_rows,
-                           w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats, win_rel);
+                           w.counters, w.st_rows, w.st_chunks, w.counters + 1, w.rec_cnt, w.fb_keys, stats, win_rel, ta);
             rc = check_launch("rescore_kernel");
             if (rc) return rc;
+            if (kRescoreFinishes) { count_launch(1); goto tail_done; }
             int sblocks = (int)imin((M + 3) / 4, (int64_t)device_sm_count() * 8);
             launch_chained(settle_kernel<G>, dim3(sblocks), dim3(128), 0, stream, mu, std, lstd, cb->cb, cb->nlpb, w.wrow, w.seg,
                            w.cand, w.rec_cnt, w.st_rows, w.st_chunks, w.counters + 1, cb->N, p.tiles, p.steps_per_cta, p.nseg, p.unit_rows, idx, zhat,
@@ -2081,6 +2130,7 @@ static int run_tc(const gq_codebook *cb, const float *mu, const float *std, cons
             count_launch(2);
         }
     }
+tail_done:
     count_launch(1);   // the search kernel
 
     // exact scan over the rows the search could not certify (device-side count, no host sync),
