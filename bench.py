@@ -95,15 +95,16 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_ms=20):
         self.gpu = gpu_index
+        self.period_ms = period_ms
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "20", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", str(self.period_ms), "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -151,17 +152,31 @@ class ClockSampler:
         return out
 
 
-def pin_to_gpu_numa(gpu_index):
-    """Bind this process to the CPUs next to its GPU before any pinned host buffer is allocated (first-touch
-    places the pages on that NUMA node).  At 8 ranks the 8 x 8 MB-per-step H2D streams otherwise share one
-    socket's memory controllers and inter-socket link; returns the CPU list or None."""
+def pin_to_gpu_numa(gpu_index, n_local=1):
+    """Bind this process to CPUs next to its GPU before any pinned host buffer is allocated (first-touch places the
+    pages on that NUMA node), and -- with several ranks on the box -- to its OWN slice of them: the ranks whose GPUs
+    share a CPU set split it evenly, so that eight launch loops of ~0.3 ms steps do not migrate over each other's
+    cores (a 0.5 ms scheduling hiccup is 10 % of a 20-step timed region).  Returns a description or None."""
     try:
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-        pynvml.nvmlDeviceSetCpuAffinity(h)
-        cpus = sorted(os.sched_getaffinity(0))
-        return f"{cpus[0]}-{cpus[-1]} ({len(cpus)} cpus)" if cpus else None
+        words = (os.cpu_count() + 63) // 64
+
+        def cpus_of(i):
+            mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(i), words)
+            return tuple(64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1)
+
+        mine = cpus_of(gpu_index)
+        if not mine:
+            return None
+        peers = [i for i in range(max(n_local, 1)) if cpus_of(i) == mine]
+        use = list(mine)
+        if len(peers) > 1 and gpu_index in peers and len(mine) >= 2 * len(peers):
+            per = len(mine) // len(peers)
+            k = peers.index(gpu_index)
+            use = list(mine[k * per:(k + 1) * per])
+        os.sched_setaffinity(0, use)
+        return f"cpus {use[0]}-{use[-1]} ({len(use)} of the {len(mine)} next to GPU {gpu_index})"
     except Exception:
         return None
 
@@ -628,13 +643,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = pin_to_gpu_numa(local_rank)
+    numa = pin_to_gpu_numa(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     ctx = Ctx(args, rank, world, local_rank)
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, 20 if world == 1 else 50)
     sampler.start()
     L = _lib.lib()
     reg = gq_b200.GaussianQuantRegularizer(format="bchw", n_samples=N_SAMPLES, group=GROUP, backend="cuda").to(dev).eval()
