@@ -41,17 +41,39 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every .cu to an object file (in parallel: gq_tc.cu alone is most of the time) and link the shared
+    library.  No relocatable device code is involved, so plain objects link."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), flush=True)
-    res = subprocess.run(cmd, cwd=str(CSRC), capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = CSRC / "_obj"
+    obj_dir.mkdir(exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src: str):
+        obj = obj_dir / (Path(src).stem + ".o")
+        cmd = [_nvcc(), *compile_flags, "-c", "-o", str(obj), str(CSRC / src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), flush=True)
+        return src, obj, subprocess.run(cmd, cwd=str(CSRC), capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    failed = False
+    for src, _, res in results:
+        if verbose or res.returncode:
+            sys.stderr.write(res.stdout + res.stderr)
+        failed |= res.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared", "-o", str(LIB),
+            *[str(o) for _, o, _ in results]]
+    res = subprocess.run(link, cwd=str(CSRC), capture_output=True, text=True)
     if verbose or res.returncode:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode:
-        raise RuntimeError(f"nvcc failed with exit code {res.returncode}")
+        raise RuntimeError(f"nvcc link failed with exit code {res.returncode}")
     return LIB
 
 
