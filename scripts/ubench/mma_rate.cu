@@ -125,6 +125,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(int n, in
     }
 }
 
+// ---- the same instruction stream with sixteen other warps reading tensor memory (tcgen05.ld ... pack::16b) all the time:
+// does the TS form keep its rate when the epilogue's loads share tensor memory with its operand fetch? ----
+__global__ void __launch_bounds__(544, 1) k3(int ts, int iters, int ld_on, unsigned long long *cycles, uint32_t *sink)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    __shared__ volatile int stop;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (65536 + 65536) / 4; i += 544) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); stop = 0; }
+    if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem = slot;
+    if (warp >= 1 && warp <= 4) {
+        uint32_t r[8];
+        for (int i = 0; i < 8; ++i) r[i] = 0x3c003c00u;
+        tmem_st_32x8(tmem + ((uint32_t)((warp - 1) * 32) << 16) + 480u, r);
+        tmem_st_wait();
+    }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t idesc = (0u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t sa = smem_u32(smem), sb = sa + 65536;
+            const uint64_t ad = mk_desc(sa, 128, 256, 0), bd = mk_desc(sb, 128, 256, 0);
+            const unsigned long long t0 = clock64();
+            for (int i = 0; i < iters; ++i) {
+                const uint32_t d = tmem + (uint32_t)((i & 1) * 128);
+                if (ts) umma_f16_ts(d, tmem + 480u, bd, idesc, 1u);
+                else umma_f16_ss(d, ad, bd, idesc, 1u);
+            }
+            umma_commit(&bar);
+            mbar_wait(&bar, 0);
+            const unsigned long long t1 = clock64();
+            cycles[blockIdx.x] = t1 - t0;
+            stop = 1;
+        }
+        __syncwarp();
+    } else if (ld_on) {
+        // 16 reader warps: lane quarter (warp - 1) % 4, 64 packed columns at (warp - 1) / 4 * 64 -- the epilogue's pattern
+        const uint32_t taddr = tmem + ((uint32_t)(((warp - 1) & 3) * 32) << 16) + (uint32_t)(((warp - 1) >> 2) * 64);
+        uint32_t acc = 0;
+        while (!stop) {
+            uint32_t v[32];
+            tmem_ld_32x64p_sync(taddr, v);
+            acc += v[(warp + acc) & 31];
+        }
+        if (acc == 0x1234567u) sink[0] = acc;
+    }
+    __syncthreads();
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 int main()
 {
     unsigned long long *cyc;
@@ -158,6 +214,18 @@ int main()
             const double per = avg / iters, ideal = 128.0 * n * 16 * 2 / 8192.0;   // per CTA: 128 rows x n columns
             printf("cta_group::2 %s M256 (128 per CTA) N%d  %s  cycles/instruction %.1f (ideal %.0f per CTA)  tensor fraction %.2f\n", ts ? "TS" : "SS", n,
                    cudaGetErrorString(e), per, ideal, ideal / per);
+        }
+    cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 65536);
+    uint32_t *sink; cudaMalloc(&sink, 4);
+    for (int ts = 0; ts < 2; ++ts)
+        for (int ld_on = 0; ld_on < 2; ++ld_on) {
+            k3<<<148, 544, 65536 + 65536>>>(ts, iters, ld_on, cyc, sink);
+            cudaError_t e = cudaDeviceSynchronize();
+            unsigned long long h[148];
+            cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+            double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
+            printf("%s M128 N128 with 16 warps %s tensor memory  %s  cycles/instruction %.1f\n", ts ? "TS" : "SS", ld_on ? "reading (tcgen05.ld x32.pack::16b loop)" : "idle on",
+                   cudaGetErrorString(e), avg / iters);
         }
     return 0;
 }
