@@ -55,22 +55,30 @@ def main():
     for w in range(32):
         if t[w].any():
             roles[w] = w
-    issuers = [17, 18]
+    ts = os.environ.get("GQ_PROF_TS") == "1"      # the TS-form kernel: epilogue 0..11 (stage = w / 4), producer 12, issuers 13..16
+    issuers = [13, 14, 15, 16] if ts else [17, 18]
+    producer = 12 if ts else 16
+    shown = (12, 13, 15, 0, 4, 8) if ts else (16, 17, 18, 0, 8, 4)
     first = min(t[w, 0, 0] for w in roles)
     print("cycles relative to the first stamp.  I = issuer (top, B tile ready + stage drained, MMAs issued, committed + warp reconverged); "
           "E = epilogue warp (top, accumulator ready, data in registers, end of iteration)")
     ev = []
     for w in sorted(roles):
-        name = f"I w{w}" if w in issuers else (f"P w{w}" if w == 16 else f"E w{w}")
-        if w not in (16, 17, 18, 0, 8, 4):
+        name = f"I w{w}" if w in issuers else (f"P w{w}" if w == producer else f"E w{w}")
+        if w not in shown:
             continue   # row block 0: its issuers (stage A / stage B) and two of its epilogue warps
         for i in range(10):
+            if t[w, i, 0] == 0:
+                continue
             ev.append((t[w, i, 0] - first, f"{name} it{300 + i}: " + " ".join(f"{int(x - first):6d}" for x in t[w, i])))
     for _, line in sorted(ev):
         print("  " + line)
     for w in sorted(roles):
-        d = np.diff(t[w, :, 0])
-        seg = [np.mean(t[w, :, k + 1] - t[w, :, k]) for k in range(3)]
+        rows = t[w][t[w, :, 0] > 0]          # (the TS-form kernel's issuers stamp every other iteration)
+        if len(rows) < 2:
+            continue
+        d = np.diff(rows[:, 0])
+        seg = [np.mean(rows[:, k + 1] - rows[:, k]) for k in range(3)]
         print(f"warp {w}: mean iteration {d.mean():.0f} cycles; segments {seg[0]:.0f} / {seg[1]:.0f} / {seg[2]:.0f}")
 
 
