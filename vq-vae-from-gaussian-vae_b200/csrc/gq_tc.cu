@@ -1671,7 +1671,7 @@ __device__ __noinline__ bool settle_row_call(int64_t r, bool full, uint32_t my_w
                          ta.steps_per_cta, nseg, ta.unit_rows, win_rel, idx_out, zhat_out);
 }
 
-struct RowIn { float w, margin, pm, ps; uint4 q; };
+struct RowIn { float w, margin, pm, ps; uint4 q; uint32_t recs; };
 
 template <int G>
 __device__ __forceinline__ RowIn fetch_row(int64_t r, int lane, const float *__restrict__ wrow,
@@ -1683,16 +1683,15 @@ __device__ __forceinline__ RowIn fetch_row(int64_t r, int lane, const float *__r
     const int seg_l = lane >> 2, quarter = lane & 3;
     in.w = __ldg(wrow + r);
     in.margin = __ldg(margin_row + r);
-    in.q = make_uint4(0xff800000u, 0u, 0xff800000u, 0u);
     // a summary counts only if its segment recorded something in THIS call (the prep kernel clears the
-    // counters, not the summaries): both loads are issued together, the select happens at the use
-    uint32_t recs = 0u;
-    uint4 q = in.q;
+    // counters, not the summaries): both loads are issued together and the select (row_summary) happens at the
+    // USE, one row later -- selecting here would park the warp on the prefetch it has just issued
+    in.recs = 0u;
+    in.q = make_uint4(0u, 0u, 0u, 0u);
     if (seg_l < nseg) {
-        recs = __ldg(rec_cnt + r * nseg + seg_l);
-        q = __ldg(reinterpret_cast<const uint4 *>(seg_hdr + r * nseg + seg_l) + quarter);
+        in.recs = __ldg(rec_cnt + r * nseg + seg_l);
+        in.q = __ldg(reinterpret_cast<const uint4 *>(seg_hdr + r * nseg + seg_l) + quarter);
     }
-    if (recs != 0u) in.q = q;
     in.pm = in.ps = 0.f;
     if (lane < G) {
         in.pm = __ldg(mu + r * G + lane);
@@ -1744,7 +1743,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
             int verdict = 0;   // 0 = decided here, 1 = settle (summaries), 2 = settle (full lists), 3 = exact scan
             int best_idx = 0;
             int n_chunks_row = 0;
-            const uint4 q = cur.q;
+            const uint4 q = cur.recs != 0u ? cur.q : make_uint4(0xff800000u, 0u, 0xff800000u, 0u);
             float gmax = head ? __uint_as_float(q.x) : -CUDART_INF_F;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
