@@ -357,6 +357,34 @@ def leg_exchange(ctx, reg, pool):
         coll = ctx.max_over_ranks(ctx.time_loop(lambda k, t=payload: gd.all_gather_indices(t, B * world), steps))[0]
         res[name] = {"value": world * M / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                      "bytes_per_rank": payload.numel() * payload.element_size(), "collective_us": coll * 1e3}
+    # the same gather as ONE kernel of ours over NVLink peer memory (pack + store into every rank's symmetric buffer,
+    # multicast stores where the switch offers them) + the symmetric-memory barrier: no NCCL on the data path
+    try:
+        items = idx.numel() // B
+        for packed_wire, want in ((True, fullp), (False, full)):
+            first = gd.PeerIndexExchange(B * world, items, reg.n_samples, packed=packed_wire)
+            exchanges = [first]
+            if first.mode == "multicast":   # also the plain peer-store form, for comparison
+                exchanges.append(gd.PeerIndexExchange(B * world, items, reg.n_samples, packed=packed_wire, use_multicast=False))
+            for px in exchanges:
+                name = f"quantize_peer_store_{'packed_u16' if packed_wire else 'int64'}_{px.mode}"
+                got = px.gather(idx)
+                same = bool(torch.equal(got.view(torch.uint8).flatten(), want.contiguous().view(torch.uint8).flatten()))
+                same = bool(ctx.max_over_ranks(0.0 if same else 1.0)[0] == 0.0)
+
+                def q_peer(k, px=px):
+                    _, inf = reg(pool[k % len(pool)])
+                    return px.gather(inf["indices"])
+
+                ms = ctx.max_over_ranks(ctx.time_loop(q_peer, steps))[0]
+                coll = ctx.max_over_ranks(ctx.time_loop(lambda k, px=px: px.gather(idx), steps))[0]
+                res[name] = {"value": world * M / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                             "bytes_per_rank": idx.numel() * px.width, "collective_us": coll * 1e3, "mode": px.mode,
+                             "equals_nccl_all_gather": same,
+                             "note": "gq_peer_gather_indices (one kernel) + symmetric-memory barrier; collective_us = the exchange alone"}
+                ok = ok and same
+    except Exception as e:   # noqa: BLE001 -- symmetric memory is optional plumbing; the NCCL records above stand
+        res["peer_store_error"] = f"{type(e).__name__}: {e}"[:300]
     # train branch: KL kernel + the one-collective fold of its partial sums (gaussian.py:83-98 over the global batch)
     z = pool[0]
     eps = torch.randn(B, CHANNELS, HW, HW, device=ctx.dev)

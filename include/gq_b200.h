@@ -24,6 +24,7 @@
  *   gq_kl_fwd/_bwd       pit/quantization/gaussian.py:76-98 (+ autograd of the same)
  *   gq_index_histogram   eval.py:127,152-154 (all_hist += torch.histogram(indices, range(0, N)))
  *   gq_usage_entropy     eval.py:137-141 (cal_ent: codebook usage and entropy of the histogram)
+ *   gq_peer_gather_indices   eval.py:167-201 (per-rank results -> all_gather), as one kernel over NVLink peer memory
  *   gq_pack_indices / gq_unpack_indices / gq_dequant_packed
  *                        no reference counterpart: the reference ships int64 indices
  *                        (gaussian.py:138,159); opt-in 16/32-bit stream, dequant as gaussian.py:162-178
@@ -40,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GQ_B200_ABI_VERSION 3
+#define GQ_B200_ABI_VERSION 4
 
 typedef void *gq_stream_t; /* cudaStream_t */
 
@@ -141,6 +142,20 @@ int gq_pack_indices(const int64_t *idx, int64_t n, int64_t N, void *packed, int3
 int gq_unpack_indices(const void *packed, int64_t n, int64_t N, int64_t *idx, gq_stream_t stream);
 int gq_dequant_packed(const gq_codebook_t *cb, const void *packed, float *out, int64_t b, int64_t l,
                       int ncb, int layout, int32_t *err_flag, gq_stream_t stream);
+
+/* ---- index exchange over NVLink peer memory ------------------------------------------------
+ * For row-sharded callers that want the whole batch's indices on every rank (the reference gathers
+ * per-rank results with all_gather, eval.py:167-201).  ONE kernel converts this rank's n int64
+ * indices to `width` bytes each (8 = unchanged, or gq_index_width(N)) and stores them at element
+ * offset elem_offset into EVERY rank's gather buffer: peer_bufs is a DEVICE array of `world` device
+ * pointers to the ranks' buffers as mapped into this process (e.g. torch symmetric memory's
+ * buffer_ptrs_dev); when mc_ptr is not NULL it is an NVSwitch multicast address of the same buffers
+ * and full 16-byte groups go out as one multimem.st each (elements outside a 16-byte group still
+ * use peer_bufs).  The call does not synchronise ranks: the caller puts its cross-rank barrier
+ * after it (and must not overwrite a buffer a peer may still read).  err_flag as gq_pack_indices. */
+int gq_peer_gather_indices(const int64_t *idx, int64_t n, int64_t N, int width, void *const *peer_bufs,
+                           void *mc_ptr, int world, int64_t elem_offset, int32_t *err_flag,
+                           gq_stream_t stream);
 
 /* ---- codebook usage ------------------------------------------------------------------------
  * gq_index_histogram: hist[idx[i]] += 1 for i < n (hist: device uint64[N], ACCUMULATED -- zero it

@@ -49,7 +49,30 @@ def _worker(rank, world, port, batch, out_dir):
     eps = torch.zeros(zs.shape[0], l, C, device=dev)
     _, _, st = gq_b200.kl_penalty(zs, eps, g, GQ_LAYOUT_BLC, target_bits=12.0, lam=1.3, lam_min=0.7, lam_max=2.0)
     glob = gd.global_kl_stats(st, zs.shape[0] * l, batch, 1.3)
+    # the same gather as one kernel of ours over NVLink peer memory (even splits), both wire widths, both phases of the
+    # double buffer, peer stores and -- where the switch offers it -- multicast stores
+    peer = {}
+    if batch % world == 0:
+        modes = [False]
+        probe = gd.PeerIndexExchange(batch, l, n_samples, packed=True, use_multicast=False)
+        if bool(getattr(probe.hdl, "has_multicast_support", False)) and int(probe.hdl.multicast_ptr) != 0:
+            modes.append(True)
+        for mc in modes:
+            for packed in (True, False):
+                px = probe if (not mc and packed) else gd.PeerIndexExchange(batch, l, n_samples, packed=packed, use_multicast=mc)
+                want = full_p if packed else full
+                ok = True
+                for _ in range(3):                                              # phases 0, 1, 0
+                    got = px.gather(info["indices"])
+                    ok = ok and got.dtype == want.dtype and bool(torch.equal(got.view(torch.uint8), want.view(torch.uint8)))
+                peer[f"{px.mode}_{'packed' if packed else 'int64'}"] = ok
+        flags = torch.tensor([float(all(peer.values()))], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)                            # every rank must have seen the right tensor
+        peer["all_ranks"] = bool(flags.item() == 1.0)
     if rank == 0:
+        import json
+        with open(os.path.join(out_dir, "peer.json"), "w") as f:
+            json.dump(peer, f)
         _, info_all = reg(z)                                                    # one process, whole batch
         _, kl_all, st_all = gq_b200.kl_penalty(z, torch.zeros(batch, l, C, device=dev), g, GQ_LAYOUT_BLC, target_bits=12.0,
                                                lam=1.3, lam_min=0.7, lam_max=2.0)
@@ -72,3 +95,8 @@ def test_nccl_sharded_rows_match_single_process(tmp_path, batch):
     assert np.array_equal(r["full_p"], r["want"]) and str(r["packed_dtype"]) == "torch.uint16"
     assert np.array_equal(r["hist"], r["hist_want"])
     np.testing.assert_allclose(r["glob"], r["ref"], rtol=1e-5)
+    import json
+    peer = json.loads((tmp_path / "peer.json").read_text())
+    if batch % world == 0:
+        assert peer and all(peer.values()), peer          # PeerIndexExchange == all_gather_indices, bit for bit
+        assert "p2p_packed" in peer and "p2p_int64" in peer

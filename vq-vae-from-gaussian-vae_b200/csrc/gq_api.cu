@@ -280,6 +280,17 @@ int gq_unpack_indices(const void *packed, int64_t n, int64_t N, int64_t *idx, gq
     return launch_unpack_indices(packed, n, N, idx, (cudaStream_t)stream);
 }
 
+int gq_peer_gather_indices(const int64_t *idx, int64_t n, int64_t N, int width, void *const *peer_bufs, void *mc_ptr,
+                           int world, int64_t elem_offset, int32_t *err_flag, gq_stream_t stream)
+{
+    if (n < 0 || N <= 0 || N > 0x7fffffffll || elem_offset < 0) { set_error("gq_peer_gather_indices: bad sizes n=%lld N=%lld offset=%lld", (long long)n, (long long)N, (long long)elem_offset); return GQ_ERR_INVALID; }
+    if (width != 8 && width != index_width(N)) { set_error("gq_peer_gather_indices: width %d is neither 8 nor gq_index_width(N) = %d", width, index_width(N)); return GQ_ERR_INVALID; }
+    if (world < 1 || world > 64) { set_error("gq_peer_gather_indices: bad world size %d", world); return GQ_ERR_INVALID; }
+    if (n == 0) return GQ_OK;
+    if (!idx || !peer_bufs) { set_error("gq_peer_gather_indices: null pointer"); return GQ_ERR_INVALID; }
+    return launch_peer_gather(idx, n, N, width, peer_bufs, mc_ptr, world, elem_offset, err_flag, (cudaStream_t)stream);
+}
+
 int gq_index_histogram(const int64_t *idx, int64_t n, int64_t N, uint64_t *hist, int32_t *err_flag, gq_stream_t stream)
 {
     if (n < 0 || N <= 0) { set_error("gq_index_histogram: bad sizes n=%lld N=%lld", (long long)n, (long long)N); return GQ_ERR_INVALID; }

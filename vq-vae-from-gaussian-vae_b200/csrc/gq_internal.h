@@ -31,6 +31,8 @@ int launch_usage_entropy(const unsigned long long *hist, int64_t N, float *out, 
 int index_width(int64_t N);
 int launch_pack_indices(const int64_t *idx, int64_t n, int64_t N, void *packed, int32_t *err_flag, cudaStream_t stream);
 int launch_unpack_indices(const void *packed, int64_t n, int64_t N, int64_t *idx, cudaStream_t stream);
+int launch_peer_gather(const int64_t *idx, int64_t n, int64_t N, int width, void *const *peer_bufs, void *mc_ptr, int world,
+                       int64_t elem_offset, int32_t *err_flag, cudaStream_t stream);
 
 // tensor-core search (gq_tc.cu)
 int64_t tc_workspace_bytes(const gq_codebook *cb, int64_t M);

@@ -175,6 +175,73 @@ unpack_indices_kernel(const P *__restrict__ packed, int64_t n, int64_t *__restri
     for (int64_t i = pairs * 2 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) idx[i] = (int64_t)packed[i];
 }
 
+// ---- index exchange over NVLink peer memory ------------------------------------------------------------
+// A sharded caller that wants the whole batch's indices on every rank (eval.py:167-201 does it with an all_gather)
+// needs, per rank, "pack my shard" followed by "deliver it to everyone".  One kernel does both: each thread converts
+// 16 output bytes worth of int64 indices and stores them at the shard's offset into EVERY rank's gather buffer --
+// through peer-mapped pointers (NVLink P2P stores), or with ONE multimem.st to an NVSwitch multicast address, which
+// the switch replicates to all ranks.  The caller orders ranks around it (torch symmetric memory's barrier).
+__device__ __forceinline__ void multimem_st_16(void *mc_addr, const uint4 &v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <typename P>
+__global__ void __launch_bounds__(256)
+peer_gather_kernel(const int64_t *__restrict__ idx, int64_t n, int64_t N, void *const *__restrict__ peer_bufs, void *mc_ptr,
+                   int world, int64_t elem_offset, int32_t *__restrict__ err_flag, bool vec)
+{
+    constexpr int V = 16 / (int)sizeof(P);   // indices per 16-byte store
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t groups = vec ? n / V : 0;
+    for (int64_t gI = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gI < groups; gI += stride) {
+        int64_t v[V];
+#pragma unroll
+        for (int k = 0; k < V / 2; ++k) {
+            const longlong2 t = __ldg(reinterpret_cast<const longlong2 *>(idx + gI * V) + k);
+            v[2 * k] = t.x;
+            v[2 * k + 1] = t.y;
+        }
+        __align__(16) P o[V];
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            bad |= v[k] < 0 || v[k] >= N;
+            o[k] = (P)v[k];
+        }
+        if (bad && err_flag) *err_flag = 1;
+        const uint4 q = *reinterpret_cast<const uint4 *>(o);
+        const int64_t at = elem_offset + gI * V;
+        if (mc_ptr) multimem_st_16(reinterpret_cast<P *>(mc_ptr) + at, q);
+        else
+            for (int p = 0; p < world; ++p) *reinterpret_cast<uint4 *>(reinterpret_cast<P *>(peer_bufs[p]) + at) = q;
+    }
+    // tail (fewer than V indices), or the whole shard when something is not 16-byte aligned: element-wise peer stores
+    for (int64_t i = groups * V + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t v = idx[i];
+        if ((v < 0 || v >= N) && err_flag) *err_flag = 1;
+        for (int p = 0; p < world; ++p) reinterpret_cast<P *>(peer_bufs[p])[elem_offset + i] = (P)v;
+    }
+}
+
+int launch_peer_gather(const int64_t *idx, int64_t n, int64_t N, int width, void *const *peer_bufs, void *mc_ptr, int world,
+                       int64_t elem_offset, int32_t *err_flag, cudaStream_t stream)
+{
+    if (n == 0) return GQ_OK;
+    const bool vec = (reinterpret_cast<uintptr_t>(idx) & 15u) == 0 && ((elem_offset * width) & 15) == 0;
+    const int per = 16 / width;
+    const int blocks = (int)imax(1, imin(((vec ? n / per : n) + 255) / 256, (int64_t)148 * 4));
+    if (width == 2)
+        peer_gather_kernel<uint16_t><<<blocks, 256, 0, stream>>>(idx, n, N, peer_bufs, mc_ptr, world, elem_offset, err_flag, vec);
+    else if (width == 4)
+        peer_gather_kernel<uint32_t><<<blocks, 256, 0, stream>>>(idx, n, N, peer_bufs, mc_ptr, world, elem_offset, err_flag, vec);
+    else
+        peer_gather_kernel<int64_t><<<blocks, 256, 0, stream>>>(idx, n, N, peer_bufs, mc_ptr, world, elem_offset, err_flag, vec);
+    count_launch();
+    return check_launch("peer_gather_kernel");
+}
+
 int index_width(int64_t N) { return N <= 65536 ? 2 : 4; }
 
 int launch_pack_indices(const int64_t *idx, int64_t n, int64_t N, void *packed, int32_t *err_flag, cudaStream_t stream)

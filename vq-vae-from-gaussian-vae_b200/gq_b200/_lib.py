@@ -19,7 +19,7 @@ GQ_OK = 0
 GQ_LAYOUT_BLC = 0
 GQ_LAYOUT_BCHW = 1
 GQ_MODE_AUTO, GQ_MODE_FAST, GQ_MODE_ROBUST = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # name -> (restype, argtypes); mirrors include/gq_b200.h one to one
 PROTOTYPES = {
@@ -48,6 +48,7 @@ PROTOTYPES = {
                            c_void_p]),
     "gq_index_width": (c_int, [c_int64]),
     "gq_pack_indices": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "gq_peer_gather_indices": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "gq_unpack_indices": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "gq_dequant_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
                                   c_void_p]),

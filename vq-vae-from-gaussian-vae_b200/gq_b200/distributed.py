@@ -14,7 +14,12 @@ single-process result on every rank:
                        deliberate improvement over the reference's rank-local lambda controller;
                        rank-local stays the default)
 
-Everything here works on whatever backend the process group uses (nccl on GPUs, gloo in the
+  PeerIndexExchange    the same gather as ONE kernel of ours over NVLink peer memory (gq_peer_gather_indices:
+                       pack + store into every rank's symmetric buffer, one multimem.st per 16 bytes where the
+                       NVSwitch offers multicast) followed by torch symmetric memory's barrier -- no NCCL on the
+                       data path; GPUs only
+
+Everything else here works on whatever backend the process group uses (nccl on GPUs, gloo in the
 CPU tests); only global_kl_stats on CUDA tensors calls into the CUDA library (its one-kernel fold).
 """
 from __future__ import annotations
@@ -113,3 +118,72 @@ def global_usage_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:
         raise RuntimeError("hist must be int64")
     dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
     return hist
+
+
+class PeerIndexExchange:
+    """all_gather of index shards without a collective library on the data path.
+
+    Every rank owns a symmetric buffer (torch.distributed._symmetric_memory: the same allocation mapped into all
+    ranks of one NVLink / NVSwitch domain) holding the whole batch's indices twice (two phases).  `gather(local)`
+    launches ONE kernel that converts this rank's int64 shard to the wire width and stores it at the shard's offset
+    into every rank's buffer -- NVLink peer stores, or one `multimem.st` per 16 bytes to the switch's multicast
+    address (`use_multicast`, default: whenever the handle offers it) -- then the symmetric-memory barrier (a signal
+    exchange on the current stream), and returns this rank's copy: the tensor `all_gather_indices` would have
+    returned.  Calls alternate between the two phases, so a result stays valid until the call after next and no
+    second barrier is needed before overwriting (a peer has passed the barrier of call t - 1 only after its stream
+    finished reading the result of call t - 2).  Even batch splits only (the shard offsets are fixed at construction).
+
+    packed=True ships gq_index_width(n_samples) bytes per index (uint16 up to 2^16 codewords) and returns that
+    dtype (`Regularizer.unpack_indices` / `dequant_packed` read it); packed=False ships and returns int64."""
+
+    def __init__(self, global_batch: int, items_per_image: int, n_samples: int, packed: bool = True, group=None,
+                 device: Optional[torch.device] = None, use_multicast: Optional[bool] = None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        from .ops import packed_dtype
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if global_batch % self.world:
+            raise ValueError(f"PeerIndexExchange needs an even split: batch {global_batch} over {self.world} ranks")
+        self.global_batch, self.items = int(global_batch), int(items_per_image)
+        self.n_samples = int(n_samples)
+        self.dtype = packed_dtype(n_samples) if packed else torch.int64
+        self.width = torch.empty(0, dtype=self.dtype).element_size()
+        self.elems = self.global_batch * self.items                      # indices of the whole batch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(self.device):
+            # bytes, so that one allocation serves every width; 16-byte aligned phases
+            self.phase_bytes = (self.elems * self.width + 255) // 256 * 256
+            self.buf = symm.empty(2 * self.phase_bytes, dtype=torch.uint8, device=self.device)
+            self.hdl = symm.rendezvous(self.buf, self.group)
+        mc = int(self.hdl.multicast_ptr) if bool(getattr(self.hdl, "has_multicast_support", False)) else 0
+        if use_multicast is None:
+            use_multicast = mc != 0
+        if use_multicast and mc == 0:
+            raise RuntimeError("this symmetric-memory handle has no multicast address")
+        self.mc_ptr = mc if use_multicast else 0
+        self.mode = "multicast" if self.mc_ptr else "p2p"
+        self.phase = 0
+        self._lib = _lib
+
+    def gather(self, local: torch.Tensor) -> torch.Tensor:
+        if local.dtype != torch.int64 or not local.is_cuda:
+            raise RuntimeError("PeerIndexExchange.gather takes this rank's int64 CUDA indices")
+        b_local = self.global_batch // self.world
+        if local.shape[0] != b_local or local.numel() != b_local * self.items:
+            raise RuntimeError(f"rank {self.rank}: shard has shape {tuple(local.shape)}, expected {b_local} images of {self.items} indices")
+        local = local.contiguous()
+        n = local.numel()
+        phase_elems = self.phase_bytes // self.width
+        offset = self.phase * phase_elems + self.rank * n
+        lib = self._lib
+        with torch.cuda.device(self.device):
+            lib.check(lib.lib().gq_peer_gather_indices(local.data_ptr(), n, self.n_samples, self.width,
+                                                       int(self.hdl.buffer_ptrs_dev), self.mc_ptr or None, self.world, offset,
+                                                       None, torch.cuda.current_stream().cuda_stream), "gq_peer_gather_indices")
+            self.hdl.barrier(channel=self.phase)      # every rank's stores have landed everywhere
+        lo = self.phase * self.phase_bytes
+        out = self.buf[lo: lo + self.elems * self.width].view(self.dtype).view((self.global_batch,) + tuple(local.shape[1:]))
+        self.phase ^= 1
+        return out
