@@ -366,8 +366,10 @@ def leg_exchange(ctx, reg, pool):
             exchanges = [first]
             if first.mode == "multicast":   # also the plain peer-store form, for comparison
                 exchanges.append(gd.PeerIndexExchange(B * world, items, reg.n_samples, packed=packed_wire, use_multicast=False))
+            if packed_wire:                 # and the two-launch form (store kernel + symmetric memory's barrier kernel)
+                exchanges.append(gd.PeerIndexExchange(B * world, items, reg.n_samples, packed=True, fused_barrier=False))
             for px in exchanges:
-                name = f"quantize_peer_store_{'packed_u16' if packed_wire else 'int64'}_{px.mode}"
+                name = f"quantize_peer_store_{'packed_u16' if packed_wire else 'int64'}_{px.mode}" + ("" if px.fused_barrier else "_two_kernels")
                 got = px.gather(idx)
                 same = bool(torch.equal(got.view(torch.uint8).flatten(), want.contiguous().view(torch.uint8).flatten()))
                 same = bool(ctx.max_over_ranks(0.0 if same else 1.0)[0] == 0.0)
@@ -381,7 +383,8 @@ def leg_exchange(ctx, reg, pool):
                 res[name] = {"value": world * M / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                              "bytes_per_rank": idx.numel() * px.width, "collective_us": coll * 1e3, "mode": px.mode,
                              "equals_nccl_all_gather": same,
-                             "note": "gq_peer_gather_indices (one kernel) + symmetric-memory barrier; collective_us = the exchange alone"}
+                             "launches": 1 if px.fused_barrier else 2,
+                             "note": "gq_peer_gather_indices_sync: pack + peer stores + cross-rank hand-shake in one kernel; collective_us = the exchange alone"}
                 ok = ok and same
     except Exception as e:   # noqa: BLE001 -- symmetric memory is optional plumbing; the NCCL records above stand
         res["peer_store_error"] = f"{type(e).__name__}: {e}"[:300]
@@ -398,6 +401,24 @@ def leg_exchange(ctx, reg, pool):
     coll = ctx.max_over_ranks(ctx.time_loop(lambda k: gd.global_kl_stats(st, M, B * world, 1.0), steps))[0]
     res["kl_fwd_plus_stat_fold"] = {"ms_per_step": ms, "collective_us": coll * 1e3, "bytes_per_rank": 32,
                                     "note": "one all_gather_into_tensor of the 8 float32 statistics per rank + the gq_kl_fold kernel"}
+    try:
+        pk = gd.PeerKlStatExchange()
+        same = bool(torch.equal(pk.fold(st, M, B * world, 1.0), gd.global_kl_stats(st, M, B * world, 1.0)))
+        same = bool(ctx.max_over_ranks(0.0 if same else 1.0)[0] == 0.0)
+
+        def kl_fold_peer(k):
+            _, _, s2 = gq_b200.kl_penalty(pool[k % len(pool)], eps, GROUP, GQ_LAYOUT_BCHW)
+            return pk.fold(s2, M, B * world, 1.0)
+
+        ms = ctx.max_over_ranks(ctx.time_loop(kl_fold_peer, steps))[0]
+        coll = ctx.max_over_ranks(ctx.time_loop(lambda k: pk.fold(st, M, B * world, 1.0), steps))[0]
+        res["kl_fwd_plus_stat_fold_peer_store"] = {"ms_per_step": ms, "collective_us": coll * 1e3, "bytes_per_rank": 32,
+                                                   "equals_nccl_fold": same,
+                                                   "launches": 1,
+                                                   "note": "gq_peer_kl_fold: peer stores + hand-shake + fold in one kernel, no NCCL"}
+        ok = ok and same
+    except Exception as e:   # noqa: BLE001
+        res["peer_fold_error"] = f"{type(e).__name__}: {e}"[:300]
     res["verified"] = ok
     res["steps"] = steps
     res["backend"] = "nccl"

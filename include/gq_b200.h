@@ -156,6 +156,23 @@ int gq_dequant_packed(const gq_codebook_t *cb, const void *packed, float *out, i
 int gq_peer_gather_indices(const int64_t *idx, int64_t n, int64_t N, int width, void *const *peer_bufs,
                            void *mc_ptr, int world, int64_t elem_offset, int32_t *err_flag,
                            gq_stream_t stream);
+/* The same with the cross-rank barrier INSIDE the kernel (one launch per exchange, no collective
+ * library): after its stores the grid's last block writes `seq` into flag slot [rank] of every
+ * rank's flag block and waits until all `world` slots of its own flag block hold >= seq; kernels
+ * that follow on the stream may read the gathered tensor.  The flag block lives at byte offset
+ * flag_offset (multiple of 16) of every rank's buffer: 64 uint32 slots + one arrival counter
+ * (272 bytes), zeroed once before the first call on all ranks.  seq starts at 1 and grows by one
+ * per call, on every rank alike.  n may be 0 (barrier only).  A rank that never makes the matching
+ * call is detected after ~4 s of polling: err_flag (may be NULL) is set to 2.
+ * gq_peer_kl_fold: global KL statistics in ONE kernel -- this rank's float[8] gq_kl_fwd statistics
+ * go to 32-byte slot [rank] at byte offset data_offset of every rank's buffer (peer stores), the
+ * same hand-shake follows, and the world-size rows are folded exactly as gq_kl_fold does. */
+int gq_peer_gather_indices_sync(const int64_t *idx, int64_t n, int64_t N, int width, void *const *peer_bufs,
+                                void *mc_ptr, int world, int rank, int64_t elem_offset, int64_t flag_offset,
+                                uint32_t seq, int32_t *err_flag, gq_stream_t stream);
+int gq_peer_kl_fold(const float *stats, void *const *peer_bufs, int world, int rank, int64_t data_offset,
+                    int64_t flag_offset, uint32_t seq, double lam, double global_batch, double total_groups,
+                    float *out4, int32_t *err_flag, gq_stream_t stream);
 
 /* ---- codebook usage ------------------------------------------------------------------------
  * gq_index_histogram: hist[idx[i]] += 1 for i < n (hist: device uint64[N], ACCUMULATED -- zero it

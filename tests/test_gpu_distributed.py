@@ -59,13 +59,20 @@ def _worker(rank, world, port, batch, out_dir):
             modes.append(True)
         for mc in modes:
             for packed in (True, False):
-                px = probe if (not mc and packed) else gd.PeerIndexExchange(batch, l, n_samples, packed=packed, use_multicast=mc)
-                want = full_p if packed else full
-                ok = True
-                for _ in range(3):                                              # phases 0, 1, 0
-                    got = px.gather(info["indices"])
-                    ok = ok and got.dtype == want.dtype and bool(torch.equal(got.view(torch.uint8), want.view(torch.uint8)))
-                peer[f"{px.mode}_{'packed' if packed else 'int64'}"] = ok
+                for fused in (True, False):     # hand-shake inside the kernel / symmetric memory's barrier kernel behind it
+                    px = probe if (not mc and packed and fused) else gd.PeerIndexExchange(
+                        batch, l, n_samples, packed=packed, use_multicast=mc, fused_barrier=fused)
+                    want = full_p if packed else full
+                    ok = True
+                    for _ in range(5):                                          # phases 0, 1, 0, 1, 0
+                        got = px.gather(info["indices"])
+                        ok = ok and got.dtype == want.dtype and bool(torch.equal(got.view(torch.uint8), want.view(torch.uint8)))
+                    ok = ok and not px.timed_out()
+                    peer[f"{px.mode}_{'packed' if packed else 'int64'}{'' if fused else '_two_kernels'}"] = ok
+        pk = gd.PeerKlStatExchange()
+        for _ in range(3):
+            got = pk.fold(st, zs.shape[0] * l, batch, 1.3)
+            peer["kl_fold"] = peer.get("kl_fold", True) and bool(torch.equal(got, glob))   # same kernel, same order: same bits
         flags = torch.tensor([float(all(peer.values()))], device=dev)
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)                            # every rank must have seen the right tensor
         peer["all_ranks"] = bool(flags.item() == 1.0)

@@ -291,6 +291,39 @@ int gq_peer_gather_indices(const int64_t *idx, int64_t n, int64_t N, int width, 
     return launch_peer_gather(idx, n, N, width, peer_bufs, mc_ptr, world, elem_offset, err_flag, (cudaStream_t)stream);
 }
 
+static int check_peer_sync(const char *fn, int world, int rank, int64_t flag_offset, uint32_t seq)
+{
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) { set_error("%s: bad rank/world %d/%d", fn, rank, world); return GQ_ERR_INVALID; }
+    if (flag_offset < 0 || (flag_offset & 15)) { set_error("%s: flag_offset must be a non-negative multiple of 16", fn); return GQ_ERR_INVALID; }
+    if (seq == 0u) { set_error("%s: seq must be >= 1 and grow by one per call", fn); return GQ_ERR_INVALID; }
+    return GQ_OK;
+}
+
+int gq_peer_gather_indices_sync(const int64_t *idx, int64_t n, int64_t N, int width, void *const *peer_bufs, void *mc_ptr,
+                                int world, int rank, int64_t elem_offset, int64_t flag_offset, uint32_t seq,
+                                int32_t *err_flag, gq_stream_t stream)
+{
+    if (n < 0 || N <= 0 || N > 0x7fffffffll || elem_offset < 0) { set_error("gq_peer_gather_indices_sync: bad sizes n=%lld N=%lld offset=%lld", (long long)n, (long long)N, (long long)elem_offset); return GQ_ERR_INVALID; }
+    if (width != 8 && width != index_width(N)) { set_error("gq_peer_gather_indices_sync: width %d is neither 8 nor gq_index_width(N) = %d", width, index_width(N)); return GQ_ERR_INVALID; }
+    int rc = check_peer_sync("gq_peer_gather_indices_sync", world, rank, flag_offset, seq);
+    if (rc) return rc;
+    if (!peer_bufs || (n > 0 && !idx)) { set_error("gq_peer_gather_indices_sync: null pointer"); return GQ_ERR_INVALID; }
+    return launch_peer_gather(idx, n, N, width, peer_bufs, mc_ptr, world, elem_offset, err_flag, (cudaStream_t)stream, rank, flag_offset, seq);
+}
+
+int gq_peer_kl_fold(const float *stats, void *const *peer_bufs, int world, int rank, int64_t data_offset, int64_t flag_offset,
+                    uint32_t seq, double lam, double global_batch, double total_groups, float *out4, int32_t *err_flag,
+                    gq_stream_t stream)
+{
+    int rc = check_peer_sync("gq_peer_kl_fold", world, rank, flag_offset, seq);
+    if (rc) return rc;
+    if (data_offset < 0 || (data_offset & 15)) { set_error("gq_peer_kl_fold: data_offset must be a non-negative multiple of 16"); return GQ_ERR_INVALID; }
+    if (!stats || !peer_bufs || !out4) { set_error("gq_peer_kl_fold: null pointer"); return GQ_ERR_INVALID; }
+    if (!(global_batch > 0.0) || !(total_groups > 0.0)) { set_error("gq_peer_kl_fold: global_batch and total_groups must be positive"); return GQ_ERR_INVALID; }
+    return launch_peer_kl_fold(stats, peer_bufs, world, rank, data_offset, flag_offset, seq, lam, global_batch,
+                               total_groups, out4, err_flag, (cudaStream_t)stream);
+}
+
 int gq_index_histogram(const int64_t *idx, int64_t n, int64_t N, uint64_t *hist, int32_t *err_flag, gq_stream_t stream)
 {
     if (n < 0 || N <= 0) { set_error("gq_index_histogram: bad sizes n=%lld N=%lld", (long long)n, (long long)N); return GQ_ERR_INVALID; }

@@ -32,7 +32,10 @@ int index_width(int64_t N);
 int launch_pack_indices(const int64_t *idx, int64_t n, int64_t N, void *packed, int32_t *err_flag, cudaStream_t stream);
 int launch_unpack_indices(const void *packed, int64_t n, int64_t N, int64_t *idx, cudaStream_t stream);
 int launch_peer_gather(const int64_t *idx, int64_t n, int64_t N, int width, void *const *peer_bufs, void *mc_ptr, int world,
-                       int64_t elem_offset, int32_t *err_flag, cudaStream_t stream);
+                       int64_t elem_offset, int32_t *err_flag, cudaStream_t stream, int rank = 0, int64_t flag_off = 0, uint32_t seq = 0);
+int launch_peer_kl_fold(const float *stats, void *const *peer_bufs, int world, int rank, int64_t data_off, int64_t flag_off,
+                        uint32_t seq, double lam, double global_batch, double total_groups, float *out4, int32_t *err_flag,
+                        cudaStream_t stream);
 
 // tensor-core search (gq_tc.cu)
 int64_t tc_workspace_bytes(const gq_codebook *cb, int64_t M);

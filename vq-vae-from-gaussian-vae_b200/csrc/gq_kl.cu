@@ -11,6 +11,7 @@
 // per block; the last block to finish reduces them in block order (deterministic).
 #include "gq_common.cuh"
 #include "gq_internal.h"
+#include "gq_ptx.cuh"
 
 namespace gq {
 
@@ -627,6 +628,55 @@ __global__ void kl_fold_kernel(const float *__restrict__ all_stats, int world, d
     out4[1] = (float)(s_kl2 / total_groups);
     out4[2] = nan_mn ? CUDART_NAN_F : mn;
     out4[3] = nan_mx ? CUDART_NAN_F : mx;
+}
+
+// The same fold with the exchange inside: ONE warp stores this rank's eight statistics into slot [rank] of every
+// rank's peer-mapped buffer (NVLink peer stores, 32 bytes each), signals / awaits every rank (peer_signal_and_wait)
+// and folds the world-size rows it now holds -- global_kl_stats as a single kernel, no collective library.
+__global__ void __launch_bounds__(64)
+peer_kl_fold_kernel(const float *__restrict__ stats, void *const *__restrict__ peer_bufs, int world, int rank, int64_t data_off,
+                    int64_t flag_off, uint32_t seq, double lam, double global_batch, double total_groups,
+                    float *__restrict__ out4, int32_t *__restrict__ err_flag)
+{
+    const int p = threadIdx.x;
+    if (p < world) {
+        const uint4 a = reinterpret_cast<const uint4 *>(stats)[0], b = reinterpret_cast<const uint4 *>(stats)[1];
+        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(peer_bufs[p]) + data_off + 32 * (int64_t)rank);
+        dst[0] = a;
+        dst[1] = b;
+        __threadfence_system();
+        if (!ptx::peer_signal_and_wait(peer_bufs, flag_off, world, rank, p, seq) && err_flag) *err_flag = 2;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const volatile float *all_stats = reinterpret_cast<const volatile float *>(reinterpret_cast<const char *>(peer_bufs[rank]) + data_off);
+    double s_kl2 = 0.0, s_wkl2 = 0.0;
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    bool nan_mn = false, nan_mx = false;
+    for (int r = 0; r < world; ++r) {
+        const volatile float *st = all_stats + 8 * r;
+        const float v2 = st[2], v3 = st[3];
+        s_kl2 += (double)st[4];
+        s_wkl2 += (double)st[5];
+        nan_mn |= v2 != v2;
+        nan_mx |= v3 != v3;
+        mn = fminf(mn, v2);
+        mx = fmaxf(mx, v3);
+    }
+    out4[0] = (float)(lam * s_wkl2 / global_batch);
+    out4[1] = (float)(s_kl2 / total_groups);
+    out4[2] = nan_mn ? CUDART_NAN_F : mn;
+    out4[3] = nan_mx ? CUDART_NAN_F : mx;
+}
+
+int launch_peer_kl_fold(const float *stats, void *const *peer_bufs, int world, int rank, int64_t data_off, int64_t flag_off,
+                        uint32_t seq, double lam, double global_batch, double total_groups, float *out4, int32_t *err_flag,
+                        cudaStream_t stream)
+{
+    peer_kl_fold_kernel<<<1, 64, 0, stream>>>(stats, peer_bufs, world, rank, data_off, flag_off, seq, lam, global_batch,
+                                              total_groups, out4, err_flag);
+    count_launch();
+    return check_launch("peer_kl_fold_kernel");
 }
 
 int launch_kl_fold(const float *all_stats, int world, double lam, double global_batch, double total_groups, float *out4,

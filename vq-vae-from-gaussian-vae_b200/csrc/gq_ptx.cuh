@@ -421,6 +421,34 @@ __device__ __forceinline__ void tmem_ld_32x256p_sync(uint32_t taddr, uint32_t (&
         : "memory");
 }
 
+// System-scope flag for cross-GPU hand-shakes over peer-mapped memory: release store (orders this thread's earlier
+// writes, fenced ones of other threads included, before the flag) and acquire load.
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Signal every rank (flag slot [rank] of rank p's flag block := seq) and wait until every rank has signalled this
+// call (own slot [p] >= seq; sequence numbers only grow, so late readers never miss one).  Threads p < world of ONE
+// block call it after the data they announce has been fenced (__threadfence_system).  Returns false on time-out
+// (a rank that never made the call): ~4 s of polling, so that a mismatched call cannot hang the GPU for good.
+__device__ __forceinline__ bool peer_signal_and_wait(void *const *peer_bufs, int64_t flag_off, int world, int rank, int p, uint32_t seq)
+{
+    uint32_t *theirs = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(peer_bufs[p]) + flag_off) + rank;
+    st_release_sys_u32(theirs, seq);
+    const uint32_t *mine = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(peer_bufs[rank]) + flag_off) + p;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys_u32(mine) - seq) < 0) {
+        if (clock64() - t0 > 8000000000ll) return false;
+    }
+    return true;
+}
+
 // packed fp16 pair maximum; ptxas fuses two dependent ones into the 3-input VHMNMX
 __device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b)
 {

@@ -14,6 +14,7 @@
 // histogram, 8 B read + 2 B written per index for the pack).
 #include "gq_common.cuh"
 #include "gq_internal.h"
+#include "gq_ptx.cuh"
 
 #include <math_constants.h>
 
@@ -190,7 +191,7 @@ __device__ __forceinline__ void multimem_st_16(void *mc_addr, const uint4 &v)
 template <typename P>
 __global__ void __launch_bounds__(256)
 peer_gather_kernel(const int64_t *__restrict__ idx, int64_t n, int64_t N, void *const *__restrict__ peer_bufs, void *mc_ptr,
-                   int world, int64_t elem_offset, int32_t *__restrict__ err_flag, bool vec)
+                   int world, int64_t elem_offset, int32_t *__restrict__ err_flag, bool vec, int rank, int64_t flag_off, uint32_t seq)
 {
     constexpr int V = 16 / (int)sizeof(P);   // indices per 16-byte store
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -223,21 +224,37 @@ peer_gather_kernel(const int64_t *__restrict__ idx, int64_t n, int64_t N, void *
         if ((v < 0 || v >= N) && err_flag) *err_flag = 1;
         for (int p = 0; p < world; ++p) reinterpret_cast<P *>(peer_bufs[p])[elem_offset + i] = (P)v;
     }
+    if (seq == 0u) return;   // the caller synchronises the ranks itself
+    // ---- cross-rank barrier inside the kernel: the LAST block of this grid announces "my shard is in your buffer" to
+    // every rank and waits for the same announcement from every rank; whatever follows on the stream may read the
+    // gathered tensor.  Flag block (in the rank's own peer-mapped buffer): 64 slots, then this grid's arrival counter.
+    __shared__ bool s_last;
+    __threadfence_system();
+    __syncthreads();
+    uint32_t *arrivals = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(peer_bufs[rank]) + flag_off) + 64;
+    if (threadIdx.x == 0) s_last = atomicAdd(arrivals, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if ((int)threadIdx.x < world && !ptx::peer_signal_and_wait(peer_bufs, flag_off, world, rank, (int)threadIdx.x, seq) && err_flag)
+        *err_flag = 2;
+    __syncthreads();
+    if (threadIdx.x == 0) *arrivals = 0u;   // for the next launch (stream-ordered)
 }
 
 int launch_peer_gather(const int64_t *idx, int64_t n, int64_t N, int width, void *const *peer_bufs, void *mc_ptr, int world,
-                       int64_t elem_offset, int32_t *err_flag, cudaStream_t stream)
+                       int64_t elem_offset, int32_t *err_flag, cudaStream_t stream, int rank, int64_t flag_off, uint32_t seq)
 {
-    if (n == 0) return GQ_OK;
+    if (n == 0 && seq == 0u) return GQ_OK;
     const bool vec = (reinterpret_cast<uintptr_t>(idx) & 15u) == 0 && ((elem_offset * width) & 15) == 0;
     const int per = 16 / width;
     const int blocks = (int)imax(1, imin(((vec ? n / per : n) + 255) / 256, (int64_t)148 * 4));
     if (width == 2)
-        peer_gather_kernel<uint16_t><<<blocks, 256, 0, stream>>>(idx, n, N, peer_bufs, mc_ptr, world, elem_offset, err_flag, vec);
+        peer_gather_kernel<uint16_t><<<blocks, 256, 0, stream>>>(idx, n, N, peer_bufs, mc_ptr, world, elem_offset, err_flag, vec, rank, flag_off, seq);
     else if (width == 4)
-        peer_gather_kernel<uint32_t><<<blocks, 256, 0, stream>>>(idx, n, N, peer_bufs, mc_ptr, world, elem_offset, err_flag, vec);
+        peer_gather_kernel<uint32_t><<<blocks, 256, 0, stream>>>(idx, n, N, peer_bufs, mc_ptr, world, elem_offset, err_flag, vec, rank, flag_off, seq);
     else
-        peer_gather_kernel<int64_t><<<blocks, 256, 0, stream>>>(idx, n, N, peer_bufs, mc_ptr, world, elem_offset, err_flag, vec);
+        peer_gather_kernel<int64_t><<<blocks, 256, 0, stream>>>(idx, n, N, peer_bufs, mc_ptr, world, elem_offset, err_flag, vec, rank, flag_off, seq);
     count_launch();
     return check_launch("peer_gather_kernel");
 }

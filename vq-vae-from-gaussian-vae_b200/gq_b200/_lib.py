@@ -49,6 +49,10 @@ PROTOTYPES = {
     "gq_index_width": (c_int, [c_int64]),
     "gq_pack_indices": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "gq_peer_gather_indices": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "gq_peer_gather_indices_sync": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64,
+                                            c_uint32, c_void_p, c_void_p]),
+    "gq_peer_kl_fold": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_uint32, c_double, c_double, c_double,
+                                c_void_p, c_void_p, c_void_p]),
     "gq_unpack_indices": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "gq_dequant_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
                                   c_void_p]),

@@ -14,10 +14,11 @@ single-process result on every rank:
                        deliberate improvement over the reference's rank-local lambda controller;
                        rank-local stays the default)
 
-  PeerIndexExchange    the same gather as ONE kernel of ours over NVLink peer memory (gq_peer_gather_indices:
+  PeerIndexExchange    the same gather as ONE kernel of ours over NVLink peer memory (gq_peer_gather_indices_sync:
                        pack + store into every rank's symmetric buffer, one multimem.st per 16 bytes where the
-                       NVSwitch offers multicast) followed by torch symmetric memory's barrier -- no NCCL on the
-                       data path; GPUs only
+                       NVSwitch offers multicast, cross-rank hand-shake by the grid's last block) -- no collective
+                       library on the data path; GPUs only
+  PeerKlStatExchange   global_kl_stats as ONE kernel (gq_peer_kl_fold: peer stores of the 32 bytes, hand-shake, fold)
 
 Everything else here works on whatever backend the process group uses (nccl on GPUs, gloo in the
 CPU tests); only global_kl_stats on CUDA tensors calls into the CUDA library (its one-kernel fold).
@@ -120,25 +121,44 @@ def global_usage_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:
     return hist
 
 
+_FLAG_BYTES = 512   # 64 uint32 flag slots + the grid's arrival counter, padded
+
+
+def _symmetric_buffer(nbytes: int, group, device):
+    """Zeroed symmetric allocation of nbytes + the flag block, mapped into every rank of the group; returns
+    (tensor, handle).  The process-group barrier after the memset keeps a fast rank from signalling into a flag
+    block its owner has not cleared yet."""
+    import torch.distributed._symmetric_memory as symm
+    with torch.cuda.device(device):
+        buf = symm.empty(nbytes + _FLAG_BYTES, dtype=torch.uint8, device=device)
+        hdl = symm.rendezvous(buf, group)
+        buf.zero_()
+        torch.cuda.synchronize(device)
+    dist.barrier(group)
+    return buf, hdl
+
+
 class PeerIndexExchange:
-    """all_gather of index shards without a collective library on the data path.
+    """all_gather of index shards as ONE kernel of this library -- no collective library on the data path.
 
     Every rank owns a symmetric buffer (torch.distributed._symmetric_memory: the same allocation mapped into all
-    ranks of one NVLink / NVSwitch domain) holding the whole batch's indices twice (two phases).  `gather(local)`
-    launches ONE kernel that converts this rank's int64 shard to the wire width and stores it at the shard's offset
-    into every rank's buffer -- NVLink peer stores, or one `multimem.st` per 16 bytes to the switch's multicast
-    address (`use_multicast`, default: whenever the handle offers it) -- then the symmetric-memory barrier (a signal
-    exchange on the current stream), and returns this rank's copy: the tensor `all_gather_indices` would have
-    returned.  Calls alternate between the two phases, so a result stays valid until the call after next and no
-    second barrier is needed before overwriting (a peer has passed the barrier of call t - 1 only after its stream
-    finished reading the result of call t - 2).  Even batch splits only (the shard offsets are fixed at construction).
+    ranks of one NVLink / NVSwitch domain) holding the whole batch's indices twice (two phases) and a flag block.
+    `gather(local)` launches gq_peer_gather_indices_sync: it converts this rank's int64 shard to the wire width,
+    stores it at the shard's offset into every rank's buffer -- NVLink peer stores, or one `multimem.st` per 16
+    bytes to the switch's multicast address (`use_multicast`, default: whenever the handle offers it) -- and its
+    last block runs the cross-rank hand-shake (release store of the call's sequence number into every rank's flag
+    block, acquire-poll of its own).  The return value is this rank's copy: the tensor `all_gather_indices` would
+    have returned.  Calls alternate between the two phases, so a result stays valid until the call after next and
+    nothing needs to be awaited before overwriting (a peer has passed the hand-shake of call t - 1 only after its
+    stream finished reading the result of call t - 2).  Even batch splits only (the shard offsets are fixed at
+    construction).  fused_barrier=False splits the exchange into the store kernel (gq_peer_gather_indices) and
+    symmetric memory's own barrier kernel.
 
     packed=True ships gq_index_width(n_samples) bytes per index (uint16 up to 2^16 codewords) and returns that
     dtype (`Regularizer.unpack_indices` / `dequant_packed` read it); packed=False ships and returns int64."""
 
     def __init__(self, global_batch: int, items_per_image: int, n_samples: int, packed: bool = True, group=None,
-                 device: Optional[torch.device] = None, use_multicast: Optional[bool] = None):
-        import torch.distributed._symmetric_memory as symm
+                 device: Optional[torch.device] = None, use_multicast: Optional[bool] = None, fused_barrier: bool = True):
         from . import _lib
         from .ops import packed_dtype
         self.group = group if group is not None else dist.group.WORLD
@@ -152,11 +172,8 @@ class PeerIndexExchange:
         self.width = torch.empty(0, dtype=self.dtype).element_size()
         self.elems = self.global_batch * self.items                      # indices of the whole batch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        with torch.cuda.device(self.device):
-            # bytes, so that one allocation serves every width; 16-byte aligned phases
-            self.phase_bytes = (self.elems * self.width + 255) // 256 * 256
-            self.buf = symm.empty(2 * self.phase_bytes, dtype=torch.uint8, device=self.device)
-            self.hdl = symm.rendezvous(self.buf, self.group)
+        self.phase_bytes = (self.elems * self.width + 255) // 256 * 256  # 16-byte aligned phases
+        self.buf, self.hdl = _symmetric_buffer(2 * self.phase_bytes, self.group, self.device)
         mc = int(self.hdl.multicast_ptr) if bool(getattr(self.hdl, "has_multicast_support", False)) else 0
         if use_multicast is None:
             use_multicast = mc != 0
@@ -164,7 +181,10 @@ class PeerIndexExchange:
             raise RuntimeError("this symmetric-memory handle has no multicast address")
         self.mc_ptr = mc if use_multicast else 0
         self.mode = "multicast" if self.mc_ptr else "p2p"
+        self.fused_barrier = bool(fused_barrier)
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.phase = 0
+        self.seq = 0
         self._lib = _lib
 
     def gather(self, local: torch.Tensor) -> torch.Tensor:
@@ -178,12 +198,63 @@ class PeerIndexExchange:
         phase_elems = self.phase_bytes // self.width
         offset = self.phase * phase_elems + self.rank * n
         lib = self._lib
+        self.seq += 1
         with torch.cuda.device(self.device):
-            lib.check(lib.lib().gq_peer_gather_indices(local.data_ptr(), n, self.n_samples, self.width,
-                                                       int(self.hdl.buffer_ptrs_dev), self.mc_ptr or None, self.world, offset,
-                                                       None, torch.cuda.current_stream().cuda_stream), "gq_peer_gather_indices")
-            self.hdl.barrier(channel=self.phase)      # every rank's stores have landed everywhere
+            stream = torch.cuda.current_stream().cuda_stream
+            if self.fused_barrier:
+                lib.check(lib.lib().gq_peer_gather_indices_sync(local.data_ptr(), n, self.n_samples, self.width,
+                                                                int(self.hdl.buffer_ptrs_dev), self.mc_ptr or None, self.world,
+                                                                self.rank, offset, 2 * self.phase_bytes, self.seq,
+                                                                self.err.data_ptr(), stream), "gq_peer_gather_indices_sync")
+            else:
+                lib.check(lib.lib().gq_peer_gather_indices(local.data_ptr(), n, self.n_samples, self.width,
+                                                           int(self.hdl.buffer_ptrs_dev), self.mc_ptr or None, self.world, offset,
+                                                           None, stream), "gq_peer_gather_indices")
+                self.hdl.barrier(channel=self.phase)      # every rank's stores have landed everywhere
         lo = self.phase * self.phase_bytes
         out = self.buf[lo: lo + self.elems * self.width].view(self.dtype).view((self.global_batch,) + tuple(local.shape[1:]))
+        self.phase ^= 1
+        return out
+
+    def timed_out(self) -> bool:
+        """True if a hand-shake gave up waiting for a rank (synchronises; for diagnostics)."""
+        return int(self.err.item()) == 2
+
+
+class PeerKlStatExchange:
+    """`global_kl_stats` as ONE kernel over NVLink peer memory (gq_peer_kl_fold): every rank stores its eight
+    gq_kl_fwd statistics (32 bytes) into slot [rank] of every rank's symmetric buffer, runs the same cross-rank
+    hand-shake as PeerIndexExchange, and folds the world-size rows it then holds exactly as gq_kl_fold does (sums
+    in double, in rank order), so every rank gets the bits `global_kl_stats` returns.  Two phases alternate."""
+
+    def __init__(self, group=None, device: Optional[torch.device] = None):
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.phase_bytes = (self.world * 32 + 255) // 256 * 256
+        self.buf, self.hdl = _symmetric_buffer(2 * self.phase_bytes, self.group, self.device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.phase = 0
+        self.seq = 0
+        self._lib = _lib
+
+    def fold(self, stats: torch.Tensor, local_groups: int, global_batch: int, lam: float,
+             total_groups: Optional[int] = None) -> torch.Tensor:
+        if stats.dtype != torch.float32 or stats.numel() != 8 or not stats.is_cuda:
+            raise RuntimeError("stats must be the float32[8] CUDA tensor gq_kl_fwd wrote")
+        if total_groups is None:
+            lo, hi = shard_bounds(global_batch, self.rank, self.world)
+            total_groups = local_groups // max(hi - lo, 1) * global_batch
+        stats = stats.contiguous()
+        lib = self._lib
+        out = torch.empty(4, dtype=torch.float32, device=stats.device)
+        self.seq += 1
+        with torch.cuda.device(self.device):
+            lib.check(lib.lib().gq_peer_kl_fold(stats.data_ptr(), int(self.hdl.buffer_ptrs_dev), self.world, self.rank,
+                                                self.phase * self.phase_bytes, 2 * self.phase_bytes, self.seq, float(lam),
+                                                float(global_batch), float(total_groups), out.data_ptr(), self.err.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "gq_peer_kl_fold")
         self.phase ^= 1
         return out
