@@ -371,6 +371,8 @@ def leg_exchange(ctx, reg, pool):
             for px in exchanges:
                 name = f"quantize_peer_store_{'packed_u16' if packed_wire else 'int64'}_{px.mode}" + ("" if px.fused_barrier else "_two_kernels")
                 got = px.gather(idx)
+                if ctx.max_over_ranks(1.0 if px.timed_out() else 0.0)[0] != 0.0:   # a rank never arrived: do not loop on it
+                    raise RuntimeError(f"{name}: cross-rank hand-shake timed out")
                 same = bool(torch.equal(got.view(torch.uint8).flatten(), want.contiguous().view(torch.uint8).flatten()))
                 same = bool(ctx.max_over_ranks(0.0 if same else 1.0)[0] == 0.0)
 
