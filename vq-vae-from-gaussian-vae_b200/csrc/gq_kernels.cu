@@ -140,6 +140,7 @@ quantize_exact_kernel(const float *__restrict__ mu, const float *__restrict__ st
             load_row<G>(nlpb + n * G, nb);
 #pragma unroll
             for (int r = 0; r < kExactRows; ++r) {
+                if (r >= rows) break;   // (block-uniform) a short row group does not pay for the empty slots
                 float t[G];
 #pragma unroll
                 for (int k = 0; k < G; ++k) {
@@ -257,6 +258,11 @@ exact_sliced_kernel(const float *__restrict__ mu, const float *__restrict__ std,
     __shared__ bool s_last;
     const int64_t total = (int64_t)(*row_count);
     const int64_t groups = (total + kExactRows - 1) / kExactRows;
+    // A handful of rows (the usual case: one row of a 65 536-row batch missed its certificate) would leave most of the
+    // grid idle with the host's slice count: cut the codebook finer so that every block gets a piece (down to one
+    // codeword per thread).  Every block derives the same number from the same device-side row count.
+    if (groups > 0)
+        slices = (int)imin(imax((int64_t)slices, (int64_t)gridDim.x / groups), (N + kExactThreads - 1) / kExactThreads);
     const int64_t per = ((N + slices - 1) / slices + kExactThreads - 1) / kExactThreads * kExactThreads;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -292,6 +298,7 @@ exact_sliced_kernel(const float *__restrict__ mu, const float *__restrict__ std,
             load_row<G>(nlpb + n * G, nb);
 #pragma unroll
             for (int r = 0; r < kExactRows; ++r) {
+                if (r >= rows) break;   // (block-uniform) a short row group does not pay for the empty slots
                 float t[G];
 #pragma unroll
                 for (int k = 0; k < G; ++k) {
