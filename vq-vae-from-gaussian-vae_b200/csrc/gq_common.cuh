@@ -174,6 +174,36 @@ inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// One row's result into the module's output tensors (FinalLayout, gq_internal.h): index element and the G channel
+// values of the codeword.  r = (bi*l + t)*ncb + j.
+template <int G>
+__device__ __forceinline__ void final_store_row(int64_t *__restrict__ idx_final, float *__restrict__ zhat_final, int64_t l, int ncb,
+                                                int layout, unsigned long long *__restrict__ usage_hist,
+                                                const float *__restrict__ cb, int64_t bi, int64_t t, int j, int64_t id)
+{
+    const int C = ncb * G;
+    if (layout == GQ_LAYOUT_BCHW) idx_final[(bi * ncb + j) * l + t] = id;
+    else idx_final[(bi * l + t) * ncb + j] = id;
+    if (usage_hist) atomicAdd(usage_hist + id, 1ull);
+    float v[G];
+    load_row<G>(cb + id * G, v);
+    if (layout == GQ_LAYOUT_BCHW) {
+        float *o = zhat_final + (bi * C + j) * l + t;
+#pragma unroll
+        for (int k = 0; k < G; ++k) o[(int64_t)k * ncb * l] = v[k];
+    } else {
+        float *o = zhat_final + (bi * l + t) * C + j;
+        if (ncb == 1 && G % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < G / 4; ++k)
+                reinterpret_cast<float4 *>(o)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < G; ++k) o[k * ncb] = v[k];
+        }
+    }
+}
+
 }  // namespace gq
 
 // opaque handle behind gq_codebook_t

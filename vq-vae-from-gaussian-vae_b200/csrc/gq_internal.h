@@ -15,9 +15,22 @@ int launch_quantize_exact(const gq_codebook *cb, const float *mu, const float *s
                           const uint32_t *row_count, int64_t *idx, float *zhat, int max_blocks,
                           cudaStream_t stream);
 
+// The module's output tensors (gaussian.py:153-158) for callers whose rows are not already in final form: indices
+// [b,l,ncb] / [b,ncb,h,w] and zhat [b,l,C] / [b,C,h,w] with channel k*ncb + j = codebook[idx][k] of row
+// r = (bi*l + t)*ncb + j.  idx_final == nullptr: nothing to do.
+struct FinalLayout {
+    int64_t *idx_final;
+    float *zhat_final;
+    int64_t b, l;
+    int ncb, layout;
+    unsigned long long *usage_hist;   // optional codebook-usage histogram (eval.py:152-154), fused
+};
+
+// `fin` (optional): the kernel also turns the row-form indices idx[] into the final tensors -- every row whose idx is
+// >= 0 in a pass of its own at the start, every listed row (idx = -1, left so) when its scan completes.
 int launch_exact_sliced(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
                         const uint32_t *row_list, const uint32_t *row_count, unsigned long long *keys,
-                        uint32_t *done, int64_t *idx, float *zhat, cudaStream_t stream);
+                        uint32_t *done, int64_t *idx, float *zhat, cudaStream_t stream, const FinalLayout *fin = nullptr);
 
 int launch_codebook_prep(gq_codebook *cb, const float *nlp_in, cudaStream_t stream);
 

@@ -242,9 +242,23 @@ exact_sliced_kernel(const float *__restrict__ mu, const float *__restrict__ std,
                     const uint32_t *__restrict__ row_list, const uint32_t *__restrict__ row_count, int slices,
                     unsigned long long *__restrict__ keys, uint32_t *__restrict__ done,
                     int64_t *__restrict__ idx_out, float *__restrict__ zhat_out, uint32_t *__restrict__ wide_dev,
-                    uint32_t *__restrict__ fb_dev, uint32_t rows_total)
+                    uint32_t *__restrict__ fb_dev, uint32_t rows_total, const FinalLayout fin)
 {
     pdl_wait();   // launched as a programmatic dependent of settle_kernel (gq_tc.cu run_tc)
+    // Last kernel of a latent call whose rows are not already in final form: row indices -> the module's output
+    // tensors (what a separate finalize launch did).  Rows on this kernel's own list carry idx = -1 and are written
+    // when their scan completes, below; the two sets are disjoint, so nothing here waits for anything.
+    if (fin.idx_final) {
+        const int64_t total_el = fin.b * fin.l * fin.ncb;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_el; i += (int64_t)gridDim.x * blockDim.x) {
+            int64_t bi, t;
+            int j;
+            if (fin.layout == GQ_LAYOUT_BCHW) { t = i % fin.l; j = (int)((i / fin.l) % fin.ncb); bi = i / (fin.l * fin.ncb); }
+            else { j = (int)(i % fin.ncb); t = (i / fin.ncb) % fin.l; bi = i / (fin.l * fin.ncb); }
+            const int64_t id = idx_out[(bi * fin.l + t) * fin.ncb + j];
+            if (id >= 0) final_store_row<G>(fin.idx_final, fin.zhat_final, fin.l, fin.ncb, fin.layout, fin.usage_hist, cb, bi, t, j, id);
+        }
+    }
     // last kernel of the call: publish how many of its rows had a plain-image window over the cap
     // (GQ_MODE_AUTO feedback, read by the host without synchronising) and reset the device word
     if (fb_dev && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -341,10 +355,17 @@ exact_sliced_kernel(const float *__restrict__ mu, const float *__restrict__ std,
             const int64_t r = s_row[tid];
             const unsigned long long key = atomicMax(&keys[r], 0ull);   // coherent read
             const int64_t bi = key ? (int64_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull)) : 0;  // all NaN: torch gives 0
-            idx_out[r] = bi;
-            if (zhat_out) {
+            if (fin.idx_final) {
+                // (idx_out[r] stays -1: the pass at the head of the kernel must never pick this row up as well)
+                const int64_t tok = r / fin.ncb;
+                final_store_row<G>(fin.idx_final, fin.zhat_final, fin.l, fin.ncb, fin.layout, fin.usage_hist, cb, tok / fin.l,
+                                   tok % fin.l, (int)(r % fin.ncb), bi);
+            } else {
+                idx_out[r] = bi;
+                if (zhat_out) {
 #pragma unroll
-                for (int k = 0; k < G; ++k) zhat_out[r * G + k] = cb[bi * G + k];
+                    for (int k = 0; k < G; ++k) zhat_out[r * G + k] = cb[bi * G + k];
+                }
             }
         }
     }
@@ -352,13 +373,14 @@ exact_sliced_kernel(const float *__restrict__ mu, const float *__restrict__ std,
 
 int launch_exact_sliced(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
                         const uint32_t *row_list, const uint32_t *row_count, unsigned long long *keys,
-                        uint32_t *done, int64_t *idx, float *zhat, cudaStream_t stream)
+                        uint32_t *done, int64_t *idx, float *zhat, cudaStream_t stream, const FinalLayout *fin)
 {
     const int slices = (int)imax(1, imin(64, cb->N / 1024));
     const int blocks = device_sm_count() * 4;
+    const FinalLayout fl = fin ? *fin : FinalLayout{nullptr, nullptr, 0, 0, 1, GQ_LAYOUT_BLC, nullptr};
 #define GQ_XS(GG) launch_chained(exact_sliced_kernel<GG>, dim3(blocks), dim3(kExactThreads), 0, stream, mu, std, lstd, cb->cb, \
         cb->nlpb, cb->N, row_list, row_count, slices, keys, done, idx, zhat, cb->wide_dev, cb->fb_dev, \
-        (uint32_t)imin(M, (int64_t)0xffffffffll))
+        (uint32_t)imin(M, (int64_t)0xffffffffll), fl)
     switch (cb->g) {
     case 1: GQ_XS(1); break;
     case 2: GQ_XS(2); break;

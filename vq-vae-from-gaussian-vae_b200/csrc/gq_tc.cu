@@ -34,7 +34,8 @@
 //                         cannot certify (window too wide, lists overflowed, non-finite values) take
 //                         the pruned exact scan along their sharpest dimension in the same kernel
 //                         (pruned_exact_row); what that cannot decide goes to
-//   5. exact_sliced_kernel (gq_kernels.cu), an exact-order full scan, through a device-side row list.
+//   5. exact_sliced_kernel (gq_kernels.cu), an exact-order full scan, through a device-side row list; for latent
+//      calls whose rows are not already in final form it also writes the module's output tensors (FinalLayout).
 //      Small calls (many segments per row) finish steps 3-4 inside rescore_many_kernel.
 //
 // Why the result is exactly the reference argmax: with E_r >= |G~[n]/s - (S_ref[n] - Q_r)| for
@@ -1650,7 +1651,7 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
         for (uint32_t it = blockIdx.x * 4 + (threadIdx.x >> 5); it < npr; it += gridDim.x * 4) {
             const int64_t r = (int64_t)pr_rows[it];
             const bool done = pruned_exact_row<G>(r, mu, std, lstd, cb, nlpb, meta, sort_val, sort_idx, N, beta, lane, idx_out, zhat_out);
-            if (!done && lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
+            if (!done && lane == 0) { fb_keys[r] = 0ull; idx_out[r] = -1; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
         }
     }
     for (uint32_t it = blockIdx.x * 4 + (threadIdx.x >> 5); it < total; it += gridDim.x * 4) {
@@ -1662,7 +1663,8 @@ settle_kernel(const float *__restrict__ mu, const float *__restrict__ std, const
         const uint32_t my_word = lane < 8 ? __ldg(row_chunks + (int64_t)it * 8 + lane) : 0u;
         const bool done = settle_row<G>(r, full, my_word, lane, mu, std, lstd, cb, nlpb, wrow, seg_hdr, cand, rec_cnt, N, tiles,
                                         steps_per_cta, nseg, unit_rows, win_rel, idx_out, zhat_out);
-        if (!done && lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
+        // (a row on the sliced scan's list carries idx = -1 until that kernel has decided it: see FinalLayout)
+        if (!done && lane == 0) { fb_keys[r] = 0ull; idx_out[r] = -1; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
     }
 }
 
@@ -1841,7 +1843,7 @@ rescore_kernel(const float *__restrict__ mu, const float *__restrict__ std, cons
                     done = settle_row_call<G>(r, verdict == 2, v, lane, mu, std, lstd, cb, wrow, seg_hdr, rec_cnt, N, nseg, win_rel,
                                               idx_out, zhat_out, ta);
                 }
-                if (!done && lane == 0) { fb_keys[r] = 0ull; ta.fb2_rows[atomicAdd(ta.fb2_count, 1u)] = (uint32_t)r; }
+                if (!done && lane == 0) { fb_keys[r] = 0ull; idx_out[r] = -1; ta.fb2_rows[atomicAdd(ta.fb2_count, 1u)] = (uint32_t)r; }
                 __syncwarp();
             } else if (verdict == 3) {
                 if (lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
@@ -2055,7 +2057,7 @@ rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std,
                 done = settle_row<G>(r, verdict == 2, v, lane, mu, std, lstd, cb, nlpb, wrow, seg_hdr, cand, rec_cnt, N, tiles,
                                      steps_per_cta, nseg, unit_rows, win_rel, idx_out, zhat_out);
             }
-            if (!done && lane == 0) { fb_keys[r] = 0ull; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
+            if (!done && lane == 0) { fb_keys[r] = 0ull; idx_out[r] = -1; fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)r; }
         }
         __syncwarp();   // s_chunks / s_par are rewritten for the next row
         st_rows += 1;
@@ -2076,7 +2078,7 @@ rescore_many_kernel(const float *__restrict__ mu, const float *__restrict__ std,
 template <int G, int KPAD, bool SPLIT>
 static int run_tc(const gq_codebook *cb, const float *mu, const float *std, const float *lstd, int64_t M,
                   int64_t *idx, float *zhat, const TcPlan &p, const TcWorkspace &w, uint32_t *stats,
-                  float w_max, cudaStream_t stream, bool do_prep = true)
+                  float w_max, cudaStream_t stream, bool do_prep = true, const FinalLayout *fin = nullptr)
 {
     using K = SearchKernel<G, KPAD, SPLIT, false>;
     static bool attr_set = false;
@@ -2153,7 +2155,7 @@ tail_done:
 
     // exact scan over the rows the search could not certify (device-side count, no host sync),
     // sliced over the codebook so that a handful of rows still spreads over the whole GPU
-    return launch_exact_sliced(cb, mu, std, lstd, M, w.fb_rows2, w.counters + 2, w.fb_keys, w.counters + 64, idx, zhat, stream);
+    return launch_exact_sliced(cb, mu, std, lstd, M, w.fb_rows2, w.counters + 2, w.fb_keys, w.counters + 64, idx, zhat, stream, fin);
 }
 
 // Debug/diagnostic path (tests only): runs row prep + the search with the DUMP epilogue and
@@ -2457,6 +2459,9 @@ int64_t latent_workspace_bytes(const gq_codebook *cb, int64_t M)
     return carve_latent(cb, M > 0 ? M : 1, nullptr).bytes;
 }
 
+#ifndef GQ_TAIL_MERGE
+#define GQ_TAIL_MERGE 1   // 0: separate finalize_kernel launch behind the exact-scan fallback (A/B)
+#endif
 static float g_w_max = 3.0f;
 
 // Which operand image a call uses (groups 8 and 16; gq_mode in gq_b200.h).  AUTO reads the feedback the
@@ -2502,6 +2507,13 @@ static int run_latent(const gq_codebook *cb, const float *z, const float *eps, i
     }
     // (log std is not materialised: the settle / exact kernels take logf(std) with the libdevice function
     // the front-end and torch use, so the values are the same bits)
+    if (GQ_TAIL_MERGE) {
+        // the last kernel of the chain (the exact-scan fallback, empty for most calls) also writes the final tensors:
+        // one launch less per call than a separate finalize pass
+        const FinalLayout fin{idx_out, zhat_out, b, l, ncb, layout, cb->usage_hist};
+        return run_tc<G, KPAD, SPLIT>(cb, lw.mu_r, lw.std_r, nullptr, M, lw.idx_rows, nullptr, p, w, stats, g_w_max, stream,
+                                      /*do_prep=*/false, &fin);
+    }
     rc = run_tc<G, KPAD, SPLIT>(cb, lw.mu_r, lw.std_r, nullptr, M, lw.idx_rows, nullptr, p, w, stats, g_w_max, stream,
                          /*do_prep=*/false);
     if (rc) return rc;
