@@ -37,7 +37,8 @@ def main():
     from gq_b200_host import host_codebook
     L = _lib.lib()
     dev = torch.device("cuda:0")
-    N, g, M = 65536, 16, 65536
+    N, g, M = 65536, 16, int(os.environ.get("GQ_PROF_ROWS", "65536"))
+    first_it = int(os.environ.get("GQ_PROF_FIRST", "300"))     # must match -DGQ_TRACE_FROM of the build
     cbn, nlp = host_codebook(N, g)
     cb = gq_b200.Codebook(torch.from_numpy(cbn).to(dev), torch.from_numpy(nlp).to(dev), 1.0)
     gen = torch.Generator().manual_seed(1)
@@ -59,7 +60,7 @@ def main():
     issuers = [13, 14, 15, 16] if ts else [17, 18]
     producer = 12 if ts else 16
     shown = (12, 13, 15, 0, 4, 8) if ts else (16, 17, 18, 0, 8, 4)
-    first = min(t[w, 0, 0] for w in roles)
+    first = 0 if first_it == 0 else min(t[w, 0, 0] for w in roles)   # small calls: cycles since the warp entered the kernel
     print("cycles relative to the first stamp.  I = issuer (top, B tile ready + stage drained, MMAs issued, committed + warp reconverged); "
           "E = epilogue warp (top, accumulator ready, data in registers, end of iteration)")
     ev = []
@@ -67,10 +68,10 @@ def main():
         name = f"I w{w}" if w in issuers else (f"P w{w}" if w == producer else f"E w{w}")
         if w not in shown:
             continue   # row block 0: its issuers (stage A / stage B) and two of its epilogue warps
-        for i in range(10):
+        for i in range(14 if first_it == 0 else 10):
             if t[w, i, 0] == 0:
                 continue
-            ev.append((t[w, i, 0] - first, f"{name} it{300 + i}: " + " ".join(f"{int(x - first):6d}" for x in t[w, i])))
+            ev.append((t[w, i, 0] - first, f"{name} it{first_it + i}: " + " ".join(f"{int(x - first):6d}" for x in t[w, i])))
     for _, line in sorted(ev):
         print("  " + line)
     for w in sorted(roles):

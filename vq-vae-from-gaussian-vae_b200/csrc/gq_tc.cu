@@ -518,7 +518,10 @@ __device__ __forceinline__ void store_a_row_smem(uint32_t a_smem, int r, const _
 
 #ifdef GQ_TC_TRACE
 // diagnostic build only (scripts/tc_prof.py): clock64 timeline of CTA 0, iterations [kTraceFrom, +kTraceN)
-constexpr int kTraceFrom = 300, kTraceN = 24;
+#ifndef GQ_TRACE_FROM
+#define GQ_TRACE_FROM 300   // first traced iteration (0 for small calls: scripts/tc_prof.py build -DGQ_TRACE_FROM=0)
+#endif
+constexpr int kTraceFrom = GQ_TRACE_FROM, kTraceN = 24;
 __device__ unsigned int g_tc_trace[32 * kTraceN * 4];
 #define GQ_TRACE_DECL() uint32_t tr_it_ = 0; const long long tr_t0_ = clock64()
 #define GQ_TRACE(slot) do { if (cta == 0 && lane == 0 && tr_it_ >= kTraceFrom && tr_it_ < kTraceFrom + kTraceN) \
