@@ -1,4 +1,6 @@
 #!/bin/bash
+# bench.py --gpus N --no-extras under torchrun (gpurun --gpus N -- 'bash scripts/bench_exchange.sh N'): prints the
+# headline and the exchange records (NCCL and peer-memory), writes gpurun_out/bench_peer_nN.json.
 mkdir -p gpurun_out
 N=${1:-2}
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 20 --warmup 5 --no-extras > gpurun_out/bench_peer_n$N.json 2> gpurun_out/bench_peer_n$N.err

@@ -1,4 +1,5 @@
 #!/bin/bash
+# The 2-rank GPU tests, then the full bench.py --gpus N line under torchrun (gpurun --gpus N -- 'bash scripts/bench_multi_gpu.sh N').
 mkdir -p gpurun_out
 N=${1:-2}
 nvidia-smi -L | head -8 | wc -l

@@ -1,5 +1,6 @@
 #!/bin/bash
-# final validation of the round: GPU suite, the driver's bench command, the ncu launch list of the same command
+# On a B200 box (gpurun -- 'bash scripts/validate_gpu.sh'): GPU suite, the driver's bench command, the ncu launch list of
+# the same command, smoke().  Writes gpurun_out/r02_*; scripts/collect_profiles.py r02 turns them into profiles/.
 mkdir -p gpurun_out
 SECONDS=0
 timeout 700 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
