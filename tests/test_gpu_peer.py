@@ -84,6 +84,33 @@ def test_peer_gather_with_in_kernel_handshake():
             assert int(errs[r].item()) == 0
 
 
+def test_peer_handshake_alone_orders_streams():
+    """n = 0: the entry point is a pure cross-rank barrier.  "Rank" 1 is held back by a long kernel on its stream;
+    "rank" 0 must not get past its hand-shake before rank 1 has made the call."""
+    L = _lib()
+    world = 2
+    bufs = [torch.zeros(256 + FLAG_BYTES, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    ptrs = _ptr_array(bufs)
+    s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
+    errs = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+    marker = torch.zeros(1, dtype=torch.int32, device="cuda")
+    seen = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    big = torch.randn(4096, 4096, device="cuda")
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        for _ in range(20):
+            big = big @ big * 1e-3          # ~ms of work ahead of rank 1's call
+        marker.fill_(1)
+        L.check(L.lib().gq_peer_gather_indices_sync(None, 0, 65536, 2, ptrs.data_ptr(), None, world, 1, 0, 256, 1,
+                                                    errs[1].data_ptr(), s1.cuda_stream), "gq_peer_gather_indices_sync")
+    with torch.cuda.stream(s0):
+        L.check(L.lib().gq_peer_gather_indices_sync(None, 0, 65536, 2, ptrs.data_ptr(), None, world, 0, 0, 256, 1,
+                                                    errs[0].data_ptr(), s0.cuda_stream), "gq_peer_gather_indices_sync")
+        seen.copy_(marker)                  # ordered behind rank 0's hand-shake
+    torch.cuda.synchronize()
+    assert int(seen.item()) == 1 and int(errs[0].item()) == 0 and int(errs[1].item()) == 0
+
+
 def test_peer_handshake_times_out_instead_of_hanging():
     """A rank whose peers never make the call gives up after a few seconds and reports it (err_flag = 2)."""
     L = _lib()
