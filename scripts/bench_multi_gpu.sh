@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 N=${1:-2}
 nvidia-smi -L | head -8 | wc -l
-timeout 300 python -m pytest tests/test_gpu_distributed.py -m gpu -x -q 2>&1 | tail -3
+[ "${SKIP_TESTS:-0}" = 1 ] || timeout 300 python -m pytest tests/test_gpu_distributed.py -m gpu -x -q 2>&1 | tail -3
 SECONDS=0
 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_full_n$N.json 2> gpurun_out/bench_full_n$N.err
 echo "bench n$N rc=$? wall: $SECONDS s"; grep -v "OMP_NUM_THREADS\|^\*\*\*" gpurun_out/bench_full_n$N.err | tail -3 | cut -c1-300
