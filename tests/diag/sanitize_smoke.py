@@ -47,5 +47,11 @@ reg=gq_b200.GaussianQuantRegularizer(format="bchw", n_samples=4096, group=16, ba
 z=torch.randn(2,32,8,8,device=dev)*0.5
 zhat,info=reg(z)
 p=reg.pack_indices(info["indices"]); h=reg.accumulate_usage(info["indices"]); print(reg.codebook_usage(h)[0].item(), torch.equal(reg.dequant(p), zhat))
+# latent call whose rows need the final-layout pass, with rows on the exact-scan list (clamped logvar extremes), g = 4 and 16
+for grp in (16, 4):
+    rg=gq_b200.GaussianQuantRegularizer(format="bchw", n_samples=4096, group=grp, backend="cuda").cuda().eval()
+    zz=torch.randn(3,32,8,8,device=dev)*0.6; zz[0,16:,0,0]=25.0; zz[0,16:,0,1]=-40.0; zz[1,16:,3,3]=-40.0
+    zq,inf=rg(zz)
+    print(" tail-merge latent call, group", grp, "dequant == zhat", torch.equal(rg.dequant(inf["indices"]), zq))
 reg.train(); zhat,info=reg(z); print(float(info["kl_loss"]))
 torch.cuda.synchronize(); print("done")
